@@ -1,0 +1,201 @@
+/*
+ * stst_workloads.h — C ABI of libstst_workloads.so: the StencilStream-B200 generation loop for a
+ * fixed set of transition functions, reachable without a C++ compiler (ctypes, cgo, JNI, ...).
+ *
+ * The reference's boundary for this path is a C++ template API, not an ABI: user code instantiates
+ * `stencil::cuda::Grid<Cell>` (reference StencilStream/cuda/Grid.hpp:50-188) and
+ * `stencil::cuda::StencilUpdate<F, split>` (reference StencilStream/cuda/StencilUpdate.hpp:41-445)
+ * with its own functor. The header-only backend in stencilstream_b200/include/StencilStream keeps
+ * that template API. This library instantiates it for the reference's example functors and its
+ * self-checking test functor, and exposes the *same object model* over C:
+ *
+ *   stst_grid_*        <- cuda::Grid<Cell>: ctor (Grid.hpp:66-74), copy_from_buffer / copy_to_buffer
+ *                         (:109-134; size mismatch -> STST_ERR_RANGE where the reference throws
+ *                         std::range_error), get_grid_height/width (:158-163), make_similar (:176)
+ *   stst_update_*      <- cuda::StencilUpdate<F>: ctor from Params (StencilUpdate.hpp:54-111),
+ *                         get_params() mutation (:152), operator() (:123-144),
+ *                         get_n_processed_cells / get_walltime / get_kernel_runtime (:160-198)
+ *
+ * Cells cross this boundary as dense row-major arrays of the C structs below ("array of structs",
+ * exactly the memory image of the reference's `sycl::buffer<Cell, 2>`); transition-function
+ * parameters cross as the stst_*_params structs below.
+ *
+ * Every function returns STST_OK or a negative STST_ERR_* code; stst_workloads_last_error() returns
+ * the message of the last failure on the calling thread. There is no CPU fallback: without a CUDA
+ * device, grid uploads and updates fail with STST_ERR_RUNTIME.
+ */
+#ifndef STST_WORKLOADS_H
+#define STST_WORKLOADS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define STST_WORKLOADS_ABI_VERSION 1
+
+#define STST_OK 0
+#define STST_ERR_UNKNOWN_WORKLOAD (-1)
+#define STST_ERR_INVALID_ARGUMENT (-2)
+#define STST_ERR_RANGE (-3)   /* std::range_error in the C++ API */
+#define STST_ERR_RUNTIME (-4) /* CUDA / runtime failure */
+
+/* ---- cell types (array-of-structs images) ------------------------------------------------------ */
+
+/* "conway": Cell = bool (1 byte, 0 or 1).  reference examples/conway/conway.cpp:35-56            */
+/* "jacobi5", "jacobi9", "jacobi_r2", "jacobi_r3": Cell = float.  examples/jacobi/kernels.hpp     */
+
+typedef struct stst_hotspot_cell { /* reference examples/hotspot/hotspot.cpp:57-62 */
+    float temp;
+    float power;
+} stst_hotspot_cell;
+
+typedef struct stst_fdtd_cell { /* reference examples/fdtd/src/material/CoefResolver.hpp:27-29 */
+    float ex, ey, hz, hz_sum;
+    float ca, cb, da, db;
+} stst_fdtd_cell;
+
+typedef struct stst_convection_cell { /* reference examples/convection/convection.cpp:36-40 */
+    double T, Pt, Vx, Vy;
+    double tau_xx, tau_yy, sigma_xy;
+    double dVxd_tau, dVyd_tau;
+    double ErrV, ErrP;
+} stst_convection_cell;
+
+typedef struct stst_kat_cell { /* reference tests/TransFuncs.hpp:36-47 */
+    int32_t r, c, i_iteration, i_subiteration;
+    int32_t status; /* 0 = Normal, 1 = Invalid, 2 = Halo */
+} stst_kat_cell;
+
+/* ---- transition-function parameters ------------------------------------------------------------- */
+
+typedef struct stst_conway_params {
+    int32_t reserved; /* the rule has no runtime parameters */
+} stst_conway_params;
+
+typedef struct stst_jacobi5_params { /* Jacobi5General::coef, examples/jacobi/kernels.hpp:265-271 */
+    float coef[5];                   /* north, west, south, east, centre */
+} stst_jacobi5_params;
+
+typedef struct stst_jacobi9_params { /* Jacobi9General::coef, examples/jacobi/kernels.hpp:303-317 */
+    float coef[3][3];
+} stst_jacobi9_params;
+
+typedef struct stst_jacobi_star_params { /* B200 addition: radius-2/3 star stencils (no reference functor) */
+    float centre;
+    float arm[3]; /* weight of the 4 cells at distance 1, 2, 3 (radius-2 variant ignores arm[2]) */
+} stst_jacobi_star_params;
+
+typedef struct stst_hotspot_params { /* HotspotKernel members, examples/hotspot/hotspot.cpp:67 */
+    float Rx_1, Ry_1, Rz_1, Cap_1;
+} stst_hotspot_params;
+
+typedef struct stst_fdtd_params { /* Kernel<CoefResolver> members, examples/fdtd/src/Kernel.hpp:130-140 */
+    float dt, t_0, tau, omega;
+    uint64_t cutoff_iteration;
+    uint64_t detect_iteration;
+    float source_radius_squared;
+    float source_r, source_c, source_distance_bound;
+    float double_center_rc;
+} stst_fdtd_params;
+
+typedef struct stst_convection_pt_params { /* PseudoTransientKernel, examples/convection/convection.cpp:82-93 */
+    uint64_t nx, ny;
+    double roh0_g_alpha;
+    double delta_eta_delta_T;
+    double eta0;
+    double deltaT;
+    double dx, dy;
+    double delta_tau_iter;
+    double beta;
+    double rho;
+    double dampX, dampY;
+    double DcT;
+} stst_convection_pt_params;
+
+typedef struct stst_convection_thermal_params { /* ThermalSolverKernel, convection.cpp:191-193 */
+    uint64_t nx, ny;
+    double dx, dy, dt;
+    double DcT;
+} stst_convection_thermal_params;
+
+typedef struct stst_kat_params {
+    int32_t reserved; /* FPGATransFunc<1> has no runtime parameters (tests/TransFuncs.hpp:55-104) */
+} stst_kat_params;
+
+/* ---- registry --------------------------------------------------------------------------------- */
+
+typedef struct stst_workload_info {
+    size_t cell_bytes;         /* sizeof(Cell)                                    */
+    size_t params_bytes;       /* sizeof(stst_<name>_params)                      */
+    size_t n_planes;           /* device planes per cell                          */
+    size_t stencil_radius;     /* F::stencil_radius                               */
+    size_t n_subiterations;    /* F::n_subiterations                              */
+    size_t bytes_per_cell_iteration; /* 2 * sizeof(Cell) * n_subiterations: the reference's own
+                                        traffic model, scripts/benchmark-common.jl:150-151 */
+} stst_workload_info;
+
+int stst_workloads_abi_version(void);
+const char *stst_workloads_last_error(void);
+int stst_workload_count(void);
+const char *stst_workload_name(int index);
+int stst_workload_get_info(const char *workload, stst_workload_info *info);
+
+/* ---- grids ---------------------------------------------------------------------------------------- */
+
+typedef struct stst_grid stst_grid;
+
+/* New, uninitialised grid of rows x cols cells of the workload's cell type. device < 0: default. */
+int stst_grid_create(const char *workload, size_t rows, size_t cols, int device, stst_grid **grid);
+/* A second handle to the same cells (Grid copy constructor). */
+int stst_grid_share(stst_grid *grid, stst_grid **other);
+int stst_grid_make_similar(stst_grid *grid, stst_grid **other);
+int stst_grid_destroy(stst_grid *grid);
+int stst_grid_shape(const stst_grid *grid, size_t *rows, size_t *cols);
+/* copy_from_buffer / copy_to_buffer: `bytes` must equal rows*cols*cell_bytes, else STST_ERR_RANGE. */
+int stst_grid_copy_from_host(stst_grid *grid, const void *cells, size_t bytes);
+int stst_grid_copy_to_host(stst_grid *grid, void *cells, size_t bytes);
+/* Force the device copy to be current (uploads a pending host image); for resident-data timing. */
+int stst_grid_sync_to_device(stst_grid *grid);
+
+/* ---- updaters ------------------------------------------------------------------------------------ */
+
+typedef struct stst_update stst_update;
+
+typedef struct stst_update_params {
+    const void *transition_function; /* -> stst_<workload>_params */
+    size_t transition_function_bytes;
+    const void *halo_value; /* -> one cell; NULL = value-initialised cell */
+    size_t halo_value_bytes;
+    size_t iteration_offset;
+    size_t n_iterations;
+    int blocking;
+    int profiling;
+    int cuda_device;           /* < 0: the source grid's device */
+    unsigned fused_iterations; /* 0 = automatic */
+    unsigned tile_rows;        /* 0 = automatic */
+} stst_update_params;
+
+typedef struct stst_update_stats {
+    size_t n_processed_cells;
+    double walltime;       /* seconds, host side                              */
+    double kernel_runtime; /* seconds, device side (profiling only, else 0)   */
+    size_t n_launches;     /* fused kernel launches so far                    */
+    unsigned fused_iterations, tile_h, tile_w, block_x, block_y, use_tma;
+    size_t smem_bytes;
+} stst_update_stats;
+
+int stst_update_create(const char *workload, const stst_update_params *params, stst_update **update);
+/* Equivalent of mutating get_params(): takes effect at the next stst_update_apply. */
+int stst_update_set_params(stst_update *update, const stst_update_params *params);
+/* operator(): *result is a new grid handle owned by the caller; `source` is not modified. */
+int stst_update_apply(stst_update *update, stst_grid *source, stst_grid **result);
+int stst_update_get_stats(stst_update *update, stst_update_stats *stats);
+int stst_update_destroy(stst_update *update);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STST_WORKLOADS_H */

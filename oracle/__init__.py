@@ -1,0 +1,84 @@
+"""TEST INFRASTRUCTURE — loader for the CPU parity oracles. Never imported by the product package.
+
+Two interchangeable implementations of `oracle_run` (same C signature):
+
+  kind "reference": oracle/_ref/liboracle_ref.so — the reference's own cpu backend and example
+                    functors compiled in place from /root/reference (built only where that tree
+                    exists; the prebuilt library travels with the repository snapshot).
+  kind "port":      oracle/liboracle_port.so — the plain-C restatement in oracle/stencil_oracle.c,
+                    buildable anywhere with gcc.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / reference arm use this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+PORT_LIB = HERE / "liboracle_port.so"
+REF_LIB = HERE / "_ref" / "liboracle_ref.so"
+
+
+class Oracle:
+    def __init__(self, path: Path):
+        self.path = path
+        self.lib = C.CDLL(str(path))
+        self.lib.oracle_run.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t]
+        self.lib.oracle_run.restype = C.c_int
+        self.lib.oracle_last_error.restype = C.c_char_p
+        self.lib.oracle_kind.restype = C.c_char_p
+        self.kind = self.lib.oracle_kind().decode()
+
+    def run(self, workload: str, params, halo, cells: np.ndarray, iteration_offset: int,
+            n_iterations: int) -> np.ndarray:
+        """Advance `cells` (2-D array of the workload's cell dtype) by `n_iterations` iterations.
+        `params`: ctypes struct (stst_<workload>_params); `halo`: one cell or None (all-zero)."""
+        cells = np.ascontiguousarray(cells)
+        out = np.empty_like(cells)
+        halo_arr = None
+        if halo is not None:
+            halo_arr = np.zeros((), dtype=cells.dtype)
+            halo_arr[()] = halo
+        status = self.lib.oracle_run(
+            workload.encode(), C.addressof(params) if params is not None else None,
+            halo_arr.ctypes.data if halo_arr is not None else None,
+            cells.ctypes.data, out.ctypes.data, cells.shape[0], cells.shape[1],
+            int(iteration_offset), int(n_iterations))
+        if status != 0:
+            raise RuntimeError(f"oracle_run({workload}) failed: "
+                               f"{self.lib.oracle_last_error().decode()}")
+        return out
+
+
+def build(verbose: bool = False) -> None:
+    """Build whatever oracle can be built on this machine."""
+    import sys
+    sys.path.insert(0, str(HERE.parent))
+    from stencilstream_b200 import _build
+    _build.build_oracle_port(verbose=verbose)
+    _build.build_oracle_ref(verbose=verbose)
+
+
+def port() -> Oracle:
+    if not PORT_LIB.exists():
+        build()
+    return Oracle(PORT_LIB)
+
+
+def reference() -> Oracle | None:
+    """The reference-built oracle, or None where it neither exists nor can be built."""
+    if not REF_LIB.exists():
+        try:
+            build()
+        except Exception:
+            return None
+    return Oracle(REF_LIB) if REF_LIB.exists() else None
+
+
+def best() -> Oracle:
+    """The reference-built oracle if available, else the C restatement."""
+    return reference() or port()

@@ -1,0 +1,179 @@
+"""Build recipes for the native parts of StencilStream-B200.
+
+Everything is built in-tree with explicit compiler invocations (nvcc for sm_100a, gcc/g++ for the CPU
+oracle) so that the resulting shared objects travel with the repository snapshot to the GPU box:
+
+  stencilstream_b200/libstst_rt.so                 C-ABI device runtime           (csrc/stst_rt.cu)
+  stencilstream_b200/libstst_workloads.so          generation loop + example functors, default flags
+  stencilstream_b200/libstst_workloads_strict.so   same, -fmad=false (bit-parity diagnosis build)
+  oracle/liboracle_port.so                         plain-C restatement of the reference algorithm
+  oracle/_ref/liboracle_ref.so                     the reference's own cpu backend + example sources,
+                                                   compiled in place from /root/reference (if present)
+
+A target is rebuilt when it is missing or older than any of its inputs.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+PKG = ROOT / "stencilstream_b200"
+ORACLE = ROOT / "oracle"
+REFERENCE = Path(os.environ.get("STST_REFERENCE_DIR", "/root/reference"))
+
+ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
+NVCC_COMMON = [
+    "-std=c++20",
+    "-O3",
+    "-lineinfo",
+    "--expt-relaxed-constexpr",
+    "-Xcompiler",
+    "-fPIC,-fvisibility=hidden",
+    "-shared",
+    f"-I{ROOT / 'include'}",
+    f"-I{PKG / 'include'}",
+    f"-I{PKG / 'compat'}",
+]
+
+
+def _nvcc() -> str:
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not Path(nvcc).exists():
+        raise RuntimeError("nvcc not found: StencilStream-B200 has no CPU fallback and cannot be built")
+    return nvcc
+
+
+def _newest(paths) -> float:
+    newest = 0.0
+    for p in paths:
+        p = Path(p)
+        if p.is_dir():
+            for q in p.rglob("*"):
+                if q.is_file():
+                    newest = max(newest, q.stat().st_mtime)
+        elif p.exists():
+            newest = max(newest, p.stat().st_mtime)
+    return newest
+
+
+def _stale(target: Path, inputs) -> bool:
+    return (not target.exists()) or target.stat().st_mtime < _newest(inputs)
+
+
+def _run(cmd, verbose: bool) -> None:
+    cmd = [str(c) for c in cmd]
+    if verbose:
+        print("+", " ".join(cmd), file=sys.stderr, flush=True)
+    proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError(f"build step failed ({proc.returncode}): {' '.join(cmd)}\n{proc.stdout}")
+    if verbose and proc.stdout.strip():
+        print(proc.stdout, file=sys.stderr)
+
+
+def build_runtime(force: bool = False, verbose: bool = False) -> Path:
+    target = PKG / "libstst_rt.so"
+    inputs = [PKG / "csrc" / "stst_rt.cu", ROOT / "include" / "stst_rt.h"]
+    if force or _stale(target, inputs):
+        _run(
+            [_nvcc(), "-std=c++20", "-O2", *ARCH_FLAGS, "-lineinfo", "-Xcompiler", "-fPIC", "-shared",
+             f"-I{ROOT / 'include'}", inputs[0], "-o", target, "-ldl"],
+            verbose,
+        )
+    return target
+
+
+def build_workloads(strict: bool = False, force: bool = False, verbose: bool = False) -> Path:
+    build_runtime(force=force, verbose=verbose)
+    target = PKG / ("libstst_workloads_strict.so" if strict else "libstst_workloads.so")
+    inputs = [PKG / "csrc" / "workloads.cu", PKG / "csrc" / "workloads", PKG / "include", PKG / "compat",
+              ROOT / "include"]
+    if force or _stale(target, inputs):
+        extra = ["-fmad=false"] if strict else []
+        _run(
+            [_nvcc(), *NVCC_COMMON, *ARCH_FLAGS, *extra, PKG / "csrc" / "workloads.cu", "-o", target,
+             f"-L{PKG}", "-lstst_rt", "-Xlinker", "-rpath,$ORIGIN"],
+            verbose,
+        )
+    return target
+
+
+def build_oracle_port(force: bool = False, verbose: bool = False) -> Path:
+    target = ORACLE / "liboracle_port.so"
+    inputs = [ORACLE / "stencil_oracle.c", ROOT / "include" / "stst_workloads.h"]
+    if force or _stale(target, inputs):
+        _run(
+            ["gcc", "-std=c11", "-O2", "-ffp-contract=off", "-fopenmp", "-fPIC", "-shared",
+             f"-I{ROOT / 'include'}", inputs[0], "-o", target, "-lm"],
+            verbose,
+        )
+    return target
+
+
+def _json_include() -> Path | None:
+    """nlohmann/json 3.11.3 (the version the reference pins) ships inside cudnn_frontend's headers."""
+    import sysconfig
+
+    candidates = [Path(sysconfig.get_paths()["purelib"]) / "include" / "cudnn_frontend" / "thirdparty"]
+    for c in candidates:
+        if (c / "nlohmann" / "json.hpp").exists():
+            return c
+    return None
+
+
+def reference_available() -> bool:
+    return (REFERENCE / "StencilStream" / "cpu" / "StencilUpdate.hpp").exists()
+
+
+_REF_GLOBALS = ["exception_handler", "description", "usage", "write_output", "read_input",
+                "save_frame"]
+
+
+def build_oracle_ref(force: bool = False, verbose: bool = False) -> Path | None:
+    """Compile the reference's own cpu backend and example functors, in place, into oracle/_ref."""
+    target = ORACLE / "_ref" / "liboracle_ref.so"
+    if not reference_available():
+        return target if target.exists() else None
+    sources = sorted((ORACLE / "ref_harness").glob("*.cpp"))
+    inputs = [*sources, ORACLE / "ref_harness", PKG / "compat", ROOT / "include" / "stst_workloads.h"]
+    if force or _stale(target, inputs):
+        target.parent.mkdir(parents=True, exist_ok=True)
+        json_inc = _json_include()
+        flags = ["-std=c++20", "-O2", "-ffp-contract=off", "-fopenmp", "-fPIC", "-w",
+                 "-fvisibility=hidden",
+                 "-DSTENCILSTREAM_BACKEND_CPU=1", f"-DSTST_REFERENCE_DIR=\"{REFERENCE}\"",
+                 f"-I{PKG / 'compat'}", f"-I{REFERENCE}", f"-I{ROOT / 'include'}",
+                 f"-I{ORACLE / 'ref_harness'}"]
+        if json_inc is not None:
+            flags.append(f"-I{json_inc}")
+        objects = []
+        for src in sources:
+            obj = target.parent / (src.stem + ".o")
+            # The example sources define same-named globals (`exception_handler`, `description`,
+            # ...): give the known ones a per-translation-unit name.
+            renames = [f"-D{name}={name}_{src.stem}" for name in _REF_GLOBALS]
+            _run(["g++", *flags, *renames, "-c", src, "-o", obj], verbose)
+            objects.append(obj)
+        _run(["g++", "-shared", "-fopenmp", *objects, "-o", target], verbose)
+    return target
+
+
+def build_all(force: bool = False, verbose: bool = False) -> dict:
+    out = {
+        "runtime": build_runtime(force=force, verbose=verbose),
+        "workloads": build_workloads(strict=False, force=force, verbose=verbose),
+        "workloads_strict": build_workloads(strict=True, force=force, verbose=verbose),
+        "oracle_port": build_oracle_port(force=force, verbose=verbose),
+        "oracle_ref": build_oracle_ref(force=force, verbose=verbose),
+    }
+    return out
+
+
+if __name__ == "__main__":
+    built = build_all(force="--force" in sys.argv, verbose=True)
+    for name, path in built.items():
+        print(f"{name}: {path}")

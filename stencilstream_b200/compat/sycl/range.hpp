@@ -1,0 +1,3 @@
+// StencilStream-B200 SYCL stand-in (reference include: StencilStream/Stencil.hpp:24).
+#pragma once
+#include "sycl.hpp"

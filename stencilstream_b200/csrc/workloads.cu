@@ -1,0 +1,357 @@
+/*
+ * libstst_workloads — instantiates the header-only B200 backend (StencilStream/cuda/*.hpp) for the
+ * transition functions in workloads/functors.hpp and exposes the resulting Grid / StencilUpdate
+ * objects through the C ABI of include/stst_workloads.h.
+ *
+ * All compute goes through stencil::cuda::StencilUpdate -> fused_sweep_kernel; nothing in this file
+ * computes cells on the host.
+ */
+#include <StencilStream/cuda/StencilUpdate.hpp>
+#include <stst_workloads.h>
+
+#include "workloads/functors.hpp"
+
+#include <cstring>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace {
+
+using namespace stst_workloads;
+namespace sc = stencil::cuda;
+
+thread_local std::string g_error;
+
+int report(int code, std::string message) {
+    g_error = std::move(message);
+    return code;
+}
+
+// ---- type-erased object model -------------------------------------------------------------------
+
+struct GridBase {
+    virtual ~GridBase() = default;
+    const char *workload = nullptr;
+    virtual std::size_t rows() const = 0;
+    virtual std::size_t cols() const = 0;
+    virtual std::size_t cell_bytes() const = 0;
+    virtual void copy_from_host(const void *cells) = 0;
+    virtual void copy_to_host(void *cells) = 0;
+    virtual void sync_to_device() = 0;
+    virtual GridBase *share() = 0;
+    virtual GridBase *make_similar() = 0;
+};
+
+template <typename Cell> struct GridHolder final : GridBase {
+    sc::Grid<Cell> grid;
+    GridHolder(const char *name, sc::Grid<Cell> g) : grid(std::move(g)) { workload = name; }
+    std::size_t rows() const override { return grid.get_grid_height(); }
+    std::size_t cols() const override { return grid.get_grid_width(); }
+    std::size_t cell_bytes() const override { return sizeof(Cell); }
+    void copy_from_host(const void *cells) override {
+        // copy_from_buffer semantics without the intermediate sycl::buffer: fill the host image.
+        typename sc::Grid<Cell>::template GridAccessor<sycl::access::mode::write> ac(grid);
+        std::memcpy(static_cast<void *>(ac.get_pointer()), cells, ac.byte_size());
+    }
+    void copy_to_host(void *cells) override {
+        typename sc::Grid<Cell>::template GridAccessor<sycl::access::mode::read> ac(grid);
+        std::memcpy(cells, static_cast<const void *>(ac.get_pointer()), ac.byte_size());
+    }
+    void sync_to_device() override {
+        grid.get_storage().require_device();
+        sc::internal::check(stst_stream_synchronize(grid.get_storage().stream), "stream sync");
+    }
+    GridBase *share() override { return new GridHolder(workload, grid); }
+    GridBase *make_similar() override { return new GridHolder(workload, grid.make_similar()); }
+};
+
+struct UpdateBase {
+    virtual ~UpdateBase() = default;
+    const char *workload = nullptr;
+    virtual void set_params(const stst_update_params &p) = 0;
+    virtual GridBase *apply(GridBase &source) = 0;
+    virtual void stats(stst_update_stats &s) = 0;
+};
+
+template <typename F, typename ParamBlock> struct UpdateHolder final : UpdateBase {
+    using Update = sc::StencilUpdate<F>;
+    using Cell = typename F::Cell;
+    std::unique_ptr<Update> update;
+
+    static typename Update::Params convert(const stst_update_params &p) {
+        if (p.transition_function_bytes != sizeof(ParamBlock) || p.transition_function == nullptr)
+            throw std::invalid_argument("transition_function_bytes does not match the workload's "
+                                        "parameter struct");
+        if (p.halo_value != nullptr && p.halo_value_bytes != sizeof(Cell))
+            throw std::invalid_argument("halo_value_bytes does not match the workload's cell type");
+        typename Update::Params out{};
+        std::memcpy(&out.transition_function.p, p.transition_function, sizeof(ParamBlock));
+        if (p.halo_value != nullptr)
+            std::memcpy(static_cast<void *>(&out.halo_value), p.halo_value, sizeof(Cell));
+        out.iteration_offset = p.iteration_offset;
+        out.n_iterations = p.n_iterations;
+        out.blocking = p.blocking != 0;
+        out.profiling = p.profiling != 0;
+        out.cuda_device = p.cuda_device;
+        out.fused_iterations = p.fused_iterations;
+        out.tile_rows = p.tile_rows;
+        return out;
+    }
+
+    UpdateHolder(const char *name, const stst_update_params &p)
+        : update(std::make_unique<Update>(convert(p))) {
+        workload = name;
+    }
+
+    void set_params(const stst_update_params &p) override { update->get_params() = convert(p); }
+
+    GridBase *apply(GridBase &source) override {
+        auto *typed = dynamic_cast<GridHolder<Cell> *>(&source);
+        if (!typed)
+            throw std::invalid_argument("grid belongs to a workload with a different cell type");
+        sc::Grid<Cell> result = (*update)(typed->grid);
+        return new GridHolder<Cell>(source.workload, result);
+    }
+
+    void stats(stst_update_stats &s) override {
+        std::memset(&s, 0, sizeof(s));
+        s.n_processed_cells = update->get_n_processed_cells();
+        s.walltime = update->get_walltime();
+        s.kernel_runtime = update->get_kernel_runtime();
+        s.n_launches = update->get_n_launches();
+        auto const &plan = update->get_last_plan();
+        s.fused_iterations = plan.fused_iterations;
+        s.tile_h = plan.tile_h;
+        s.tile_w = plan.tile_w;
+        s.block_x = plan.block_x;
+        s.block_y = plan.block_y;
+        s.use_tma = plan.use_tma ? 1u : 0u;
+        s.smem_bytes = plan.smem_bytes;
+    }
+};
+
+struct WorkloadEntry {
+    const char *name;
+    stst_workload_info info;
+    GridBase *(*make_grid)(const char *, std::size_t, std::size_t, int);
+    UpdateBase *(*make_update)(const char *, const stst_update_params &);
+};
+
+template <typename F, typename ParamBlock> WorkloadEntry make_entry(const char *name) {
+    using Cell = typename F::Cell;
+    WorkloadEntry e{};
+    e.name = name;
+    e.info.cell_bytes = sizeof(Cell);
+    e.info.params_bytes = sizeof(ParamBlock);
+    e.info.n_planes = sc::internal::CellLayout<Cell>::n_planes;
+    e.info.stencil_radius = F::stencil_radius;
+    e.info.n_subiterations = F::n_subiterations;
+    e.info.bytes_per_cell_iteration = 2 * sizeof(Cell) * F::n_subiterations;
+    e.make_grid = [](const char *n, std::size_t r, std::size_t c, int device) -> GridBase * {
+        if (device < 0)
+            device = sc::internal::default_device_ordinal();
+        return new GridHolder<Cell>(n, sc::Grid<Cell>(r, c, device));
+    };
+    e.make_update = [](const char *n, const stst_update_params &p) -> UpdateBase * {
+        return new UpdateHolder<F, ParamBlock>(n, p);
+    };
+    return e;
+}
+
+const std::vector<WorkloadEntry> &registry() {
+    static const std::vector<WorkloadEntry> entries = {
+        make_entry<ConwayRule, stst_conway_params>("conway"),
+        make_entry<Jacobi5Rule, stst_jacobi5_params>("jacobi5"),
+        make_entry<Jacobi9Rule, stst_jacobi9_params>("jacobi9"),
+        make_entry<JacobiStarRule<2>, stst_jacobi_star_params>("jacobi_r2"),
+        make_entry<JacobiStarRule<3>, stst_jacobi_star_params>("jacobi_r3"),
+        make_entry<HotspotRule, stst_hotspot_params>("hotspot"),
+        make_entry<FdtdCoefRule, stst_fdtd_params>("fdtd"),
+        make_entry<ConvectionPseudoTransientRule, stst_convection_pt_params>("convection_pt"),
+        make_entry<ConvectionThermalRule, stst_convection_thermal_params>("convection_thermal"),
+        make_entry<KatRule<1>, stst_kat_params>("kat"),
+        make_entry<KatRule<2>, stst_kat_params>("kat_r2"),
+    };
+    return entries;
+}
+
+const WorkloadEntry *find(const char *name) {
+    if (!name)
+        return nullptr;
+    for (auto const &e : registry())
+        if (std::strcmp(e.name, name) == 0)
+            return &e;
+    return nullptr;
+}
+
+template <typename Fn> int guarded(Fn &&fn) {
+    try {
+        return fn();
+    } catch (std::range_error const &e) {
+        return report(STST_ERR_RANGE, e.what());
+    } catch (std::invalid_argument const &e) {
+        return report(STST_ERR_INVALID_ARGUMENT, e.what());
+    } catch (std::exception const &e) {
+        return report(STST_ERR_RUNTIME, e.what());
+    } catch (...) {
+        return report(STST_ERR_RUNTIME, "unknown exception");
+    }
+}
+
+} // namespace
+
+struct stst_grid {
+    std::unique_ptr<GridBase> impl;
+};
+struct stst_update {
+    std::unique_ptr<UpdateBase> impl;
+};
+
+#define STST_EXPORT extern "C" __attribute__((visibility("default")))
+
+STST_EXPORT int stst_workloads_abi_version(void) { return STST_WORKLOADS_ABI_VERSION; }
+
+STST_EXPORT const char *stst_workloads_last_error(void) { return g_error.c_str(); }
+
+STST_EXPORT int stst_workload_count(void) { return int(registry().size()); }
+
+STST_EXPORT const char *stst_workload_name(int index) {
+    if (index < 0 || index >= int(registry().size()))
+        return nullptr;
+    return registry()[index].name;
+}
+
+STST_EXPORT int stst_workload_get_info(const char *workload, stst_workload_info *info) {
+    const WorkloadEntry *e = find(workload);
+    if (!e)
+        return report(STST_ERR_UNKNOWN_WORKLOAD, std::string("unknown workload: ") +
+                                                     (workload ? workload : "(null)"));
+    if (!info)
+        return report(STST_ERR_INVALID_ARGUMENT, "info is null");
+    *info = e->info;
+    return STST_OK;
+}
+
+STST_EXPORT int stst_grid_create(const char *workload, size_t rows, size_t cols, int device,
+                                 stst_grid **grid) {
+    const WorkloadEntry *e = find(workload);
+    if (!e)
+        return report(STST_ERR_UNKNOWN_WORKLOAD, std::string("unknown workload: ") +
+                                                     (workload ? workload : "(null)"));
+    if (!grid)
+        return report(STST_ERR_INVALID_ARGUMENT, "grid is null");
+    return guarded([&] {
+        *grid = new stst_grid{std::unique_ptr<GridBase>(e->make_grid(e->name, rows, cols, device))};
+        return STST_OK;
+    });
+}
+
+STST_EXPORT int stst_grid_share(stst_grid *grid, stst_grid **other) {
+    if (!grid || !other)
+        return report(STST_ERR_INVALID_ARGUMENT, "null argument");
+    return guarded([&] {
+        *other = new stst_grid{std::unique_ptr<GridBase>(grid->impl->share())};
+        return STST_OK;
+    });
+}
+
+STST_EXPORT int stst_grid_make_similar(stst_grid *grid, stst_grid **other) {
+    if (!grid || !other)
+        return report(STST_ERR_INVALID_ARGUMENT, "null argument");
+    return guarded([&] {
+        *other = new stst_grid{std::unique_ptr<GridBase>(grid->impl->make_similar())};
+        return STST_OK;
+    });
+}
+
+STST_EXPORT int stst_grid_destroy(stst_grid *grid) {
+    delete grid;
+    return STST_OK;
+}
+
+STST_EXPORT int stst_grid_shape(const stst_grid *grid, size_t *rows, size_t *cols) {
+    if (!grid || !rows || !cols)
+        return report(STST_ERR_INVALID_ARGUMENT, "null argument");
+    *rows = grid->impl->rows();
+    *cols = grid->impl->cols();
+    return STST_OK;
+}
+
+STST_EXPORT int stst_grid_copy_from_host(stst_grid *grid, const void *cells, size_t bytes) {
+    if (!grid || (!cells && bytes != 0))
+        return report(STST_ERR_INVALID_ARGUMENT, "null argument");
+    if (bytes != grid->impl->rows() * grid->impl->cols() * grid->impl->cell_bytes())
+        return report(STST_ERR_RANGE, "The target buffer has not the same size as the grid");
+    return guarded([&] {
+        grid->impl->copy_from_host(cells);
+        return STST_OK;
+    });
+}
+
+STST_EXPORT int stst_grid_copy_to_host(stst_grid *grid, void *cells, size_t bytes) {
+    if (!grid || (!cells && bytes != 0))
+        return report(STST_ERR_INVALID_ARGUMENT, "null argument");
+    if (bytes != grid->impl->rows() * grid->impl->cols() * grid->impl->cell_bytes())
+        return report(STST_ERR_RANGE, "The target buffer has not the same size as the grid");
+    return guarded([&] {
+        grid->impl->copy_to_host(cells);
+        return STST_OK;
+    });
+}
+
+STST_EXPORT int stst_grid_sync_to_device(stst_grid *grid) {
+    if (!grid)
+        return report(STST_ERR_INVALID_ARGUMENT, "null argument");
+    return guarded([&] {
+        grid->impl->sync_to_device();
+        return STST_OK;
+    });
+}
+
+STST_EXPORT int stst_update_create(const char *workload, const stst_update_params *params,
+                                   stst_update **update) {
+    const WorkloadEntry *e = find(workload);
+    if (!e)
+        return report(STST_ERR_UNKNOWN_WORKLOAD, std::string("unknown workload: ") +
+                                                     (workload ? workload : "(null)"));
+    if (!params || !update)
+        return report(STST_ERR_INVALID_ARGUMENT, "null argument");
+    return guarded([&] {
+        *update = new stst_update{std::unique_ptr<UpdateBase>(e->make_update(e->name, *params))};
+        return STST_OK;
+    });
+}
+
+STST_EXPORT int stst_update_set_params(stst_update *update, const stst_update_params *params) {
+    if (!update || !params)
+        return report(STST_ERR_INVALID_ARGUMENT, "null argument");
+    return guarded([&] {
+        update->impl->set_params(*params);
+        return STST_OK;
+    });
+}
+
+STST_EXPORT int stst_update_apply(stst_update *update, stst_grid *source, stst_grid **result) {
+    if (!update || !source || !result)
+        return report(STST_ERR_INVALID_ARGUMENT, "null argument");
+    return guarded([&] {
+        *result = new stst_grid{std::unique_ptr<GridBase>(update->impl->apply(*source->impl))};
+        return STST_OK;
+    });
+}
+
+STST_EXPORT int stst_update_get_stats(stst_update *update, stst_update_stats *stats) {
+    if (!update || !stats)
+        return report(STST_ERR_INVALID_ARGUMENT, "null argument");
+    return guarded([&] {
+        update->impl->stats(*stats);
+        return STST_OK;
+    });
+}
+
+STST_EXPORT int stst_update_destroy(stst_update *update) {
+    delete update;
+    return STST_OK;
+}

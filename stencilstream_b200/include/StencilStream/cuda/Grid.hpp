@@ -1,0 +1,351 @@
+/*
+ * StencilStream-B200 — `stencil::cuda::Grid<Cell>`: a two-dimensional grid that lives in B200 HBM.
+ *
+ * Drop-in for the reference's `stencil::cuda::Grid` (reference StencilStream/cuda/Grid.hpp:50-188):
+ * same constructors, `copy_from_buffer` / `copy_to_buffer` (throwing `std::range_error` on a size
+ * mismatch), nested `GridAccessor<mode>`, `get_grid_height/width/range`, `make_similar`, and the
+ * same *handle* semantics — copying a Grid yields a second reference to the same cells
+ * (reference Grid.hpp:97).
+ *
+ * What is different underneath: the reference keeps an array-of-structs `sycl::buffer<Cell, 2>` and
+ * lets the SYCL runtime migrate it. Here the device copy is a set of row-major planes, one per
+ * `Cell::fields` entry (see cuda/internal/Helpers.hpp), each row padded to 128 bytes, allocated from
+ * the runtime's stream-ordered pool; the host copy is a lazily created pinned array-of-structs
+ * mirror that only exists once host code asks for a `GridAccessor` or a buffer copy. Transfers
+ * between the two are explicit (chunked pinned copies plus a layout-conversion kernel) and happen
+ * at the same points where SYCL would migrate: accessor construction and the next update.
+ */
+#pragma once
+#include "internal/Helpers.hpp"
+#include "internal/Runtime.hpp"
+#include "internal/TileKernel.hpp"
+
+#include <sycl/sycl.hpp>
+
+#include <algorithm>
+#include <cstring>
+#include <memory>
+#include <stdexcept>
+
+namespace stencil {
+namespace cuda {
+
+namespace internal {
+
+/// Device ordinal used by grids and updaters that were not told otherwise (env STST_DEVICE, else 0).
+inline int default_device_ordinal() {
+    if (const char *env = std::getenv("STST_DEVICE"))
+        return std::atoi(env);
+    return 0;
+}
+
+/**
+ * Shared state behind all handles to one grid: the device planes, the optional pinned host
+ * mirror, and which of the two currently holds the authoritative contents.
+ */
+template <typename Cell> class GridStorage {
+  public:
+    using Layout = CellLayout<Cell>;
+
+    GridStorage(std::size_t height, std::size_t width, int device)
+        : height(height), width(width), device(device), stream(default_stream(device)),
+          planes{}, device_block(nullptr), host(nullptr), host_current(true),
+          device_current(true) {
+        if (height > 0x7fffffffull || width > 0x7fffffffull)
+            throw std::range_error("StencilStream-B200 grids are limited to 2^31-1 rows/columns");
+    }
+
+    GridStorage(GridStorage const &) = delete;
+    GridStorage &operator=(GridStorage const &) = delete;
+
+    ~GridStorage() {
+        device_free(device, device_block, stream);
+        if (host) {
+            // The mirror may still be the source/target of an in-flight copy.
+            (void)stst_stream_synchronize(stream);
+            pinned_free(host);
+        }
+    }
+
+    /// Elements between consecutive rows of plane `i` (row byte pitch is a multiple of 128).
+    static std::size_t plane_pitch(std::size_t i, std::size_t width) {
+        const std::size_t elem = Layout::plane_bytes(i);
+        // Smallest element count whose byte size is a multiple of both `elem` and 128.
+        std::size_t pitch = std::max<std::size_t>(width, 1);
+        while ((pitch * elem) % 128 != 0)
+            pitch++;
+        return pitch;
+    }
+
+    /// Make sure the device planes exist (contents unspecified if they had to be created).
+    void allocate_device() {
+        if (device_block)
+            return;
+        std::size_t offsets[Layout::n_planes];
+        std::size_t total = 0;
+        for (std::size_t i = 0; i < Layout::n_planes; i++) {
+            offsets[i] = total;
+            const std::size_t bytes =
+                plane_pitch(i, width) * std::max<std::size_t>(height, 1) * Layout::plane_bytes(i);
+            total += (bytes + 255) / 256 * 256;
+        }
+        device_block = device_alloc(device, total, stream);
+        for (std::size_t i = 0; i < Layout::n_planes; i++) {
+            planes.base[i] = static_cast<unsigned char *>(device_block) + offsets[i];
+            planes.pitch[i] = plane_pitch(i, width);
+        }
+    }
+
+    void allocate_host() {
+        if (!host)
+            host = static_cast<Cell *>(pinned_alloc(std::max<std::size_t>(n_cells(), 1) * sizeof(Cell)));
+    }
+
+    std::size_t n_cells() const { return height * width; }
+
+    /// Bring the device planes up to date (uploading the host mirror if that is newer).
+    void require_device() {
+        allocate_device();
+        if (!device_current) {
+            upload();
+            device_current = true;
+        }
+    }
+
+    /// Bring the host mirror up to date (downloading the planes if those are newer).
+    void require_host() {
+        allocate_host();
+        if (!host_current) {
+            download();
+            host_current = true;
+        }
+    }
+
+    /// The device planes were (or are being, in stream order) overwritten.
+    void device_written() {
+        device_current = true;
+        host_current = false;
+    }
+
+    /// The host mirror was handed out for writing.
+    void host_written() {
+        host_current = true;
+        device_current = false;
+    }
+
+    const std::size_t height, width;
+    const int device;
+    const stst_stream_t stream;
+    PlaneSet planes;
+
+  private:
+    static constexpr std::size_t staging_bytes = std::size_t(64) << 20;
+
+    std::size_t rows_per_chunk() const {
+        const std::size_t row_bytes = std::max<std::size_t>(width * sizeof(Cell), 1);
+        return std::max<std::size_t>(1, std::min<std::size_t>(height, staging_bytes / row_bytes));
+    }
+
+    void upload() {
+        if (n_cells() == 0)
+            return;
+        if constexpr (!Layout::is_split) {
+            STST_RT_CHECK(stst_memcpy_2d_async(planes.base[0], planes.pitch[0] * sizeof(Cell), host,
+                                               width * sizeof(Cell), width * sizeof(Cell), height,
+                                               /*h2d*/ 0, stream));
+        } else {
+            const std::size_t chunk_rows = rows_per_chunk();
+            void *staging[2] = {device_alloc(device, chunk_rows * width * sizeof(Cell), stream),
+                                device_alloc(device, chunk_rows * width * sizeof(Cell), stream)};
+            std::size_t chunk = 0;
+            for (std::size_t row = 0; row < height; row += chunk_rows, chunk++) {
+                const std::size_t rows = std::min(chunk_rows, height - row);
+                const std::size_t cells = rows * width;
+                void *stage = staging[chunk & 1];
+                STST_RT_CHECK(stst_memcpy_h2d_async(stage, host + row * width, cells * sizeof(Cell),
+                                                    stream));
+                launch_layout_kernel</*scatter=*/true>(static_cast<Cell *>(stage), row, cells);
+            }
+            device_free(device, staging[0], stream);
+            device_free(device, staging[1], stream);
+        }
+        // The caller may modify the mirror right after an accessor is gone: finish reading it now.
+        STST_RT_CHECK(stst_stream_synchronize(stream));
+    }
+
+    void download() {
+        if (n_cells() == 0)
+            return;
+        if constexpr (!Layout::is_split) {
+            STST_RT_CHECK(stst_memcpy_2d_async(host, width * sizeof(Cell), planes.base[0],
+                                               planes.pitch[0] * sizeof(Cell), width * sizeof(Cell),
+                                               height, /*d2h*/ 1, stream));
+        } else {
+            const std::size_t chunk_rows = rows_per_chunk();
+            void *staging[2] = {device_alloc(device, chunk_rows * width * sizeof(Cell), stream),
+                                device_alloc(device, chunk_rows * width * sizeof(Cell), stream)};
+            std::size_t chunk = 0;
+            for (std::size_t row = 0; row < height; row += chunk_rows, chunk++) {
+                const std::size_t rows = std::min(chunk_rows, height - row);
+                const std::size_t cells = rows * width;
+                void *stage = staging[chunk & 1];
+                launch_layout_kernel</*scatter=*/false>(static_cast<Cell *>(stage), row, cells);
+                STST_RT_CHECK(stst_memcpy_d2h_async(host + row * width, stage, cells * sizeof(Cell),
+                                                    stream));
+            }
+            device_free(device, staging[0], stream);
+            device_free(device, staging[1], stream);
+        }
+        STST_RT_CHECK(stst_stream_synchronize(stream));
+    }
+
+    template <bool scatter>
+    void launch_layout_kernel(Cell *staging, std::size_t plane_row0, std::size_t cells) {
+#if defined(__CUDACC__)
+        const unsigned block = 256;
+        const unsigned grid =
+            unsigned(std::min<std::size_t>((cells + block - 1) / block, std::size_t(148) * 16));
+        if constexpr (scatter) {
+            scatter_cells_kernel<Cell><<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
+                staging, planes, width, plane_row0, cells);
+        } else {
+            gather_cells_kernel<Cell><<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
+                staging, planes, width, plane_row0, cells);
+        }
+        cudaError_t err = cudaGetLastError();
+        if (err != cudaSuccess)
+            throw std::runtime_error(std::string("StencilStream-B200: layout kernel launch failed: ") +
+                                     cudaGetErrorString(err));
+#else
+        (void)staging;
+        (void)plane_row0;
+        (void)cells;
+        throw std::runtime_error("StencilStream-B200 must be compiled with nvcc for sm_100a; "
+                                 "there is no CPU fallback");
+#endif
+    }
+
+    void *device_block;
+    Cell *host;
+    bool host_current, device_current;
+
+  public:
+    Cell *host_data() { return host; }
+};
+
+} // namespace internal
+
+template <typename Cell> class Grid {
+  public:
+    /// Number of grid dimensions.
+    static constexpr std::size_t dimensions = 2;
+
+    /// New, uninitialised grid of `r` rows and `c` columns.
+    Grid(std::size_t r, std::size_t c)
+        : storage(std::make_shared<Storage>(r, c, internal::default_device_ordinal())) {}
+
+    /// New, uninitialised grid; `range[0]` rows, `range[1]` columns.
+    Grid(sycl::range<2> range) : Grid(range[0], range[1]) {}
+
+    /// New grid with the extent and contents of `other_buffer`.
+    Grid(sycl::buffer<Cell, 2> other_buffer) : Grid(other_buffer.get_range()) {
+        copy_from_buffer(other_buffer);
+    }
+
+    /// A further handle to the cells of `other_grid` (no copy).
+    Grid(Grid const &other_grid) = default;
+    Grid &operator=(Grid const &other_grid) = default;
+
+    /// B200 extension: new, uninitialised grid on a specific CUDA device.
+    Grid(std::size_t r, std::size_t c, int cuda_device)
+        : storage(std::make_shared<Storage>(r, c, cuda_device)) {}
+
+    /// Overwrite the grid with the contents of the equally-sized `other_buffer`.
+    void copy_from_buffer(sycl::buffer<Cell, 2> other_buffer) {
+        if (get_grid_range() != other_buffer.get_range()) {
+            throw std::range_error("The target buffer has not the same size as the grid");
+        }
+        storage->allocate_host();
+        sycl::host_accessor other_ac(other_buffer, sycl::read_only);
+        std::memcpy(static_cast<void *>(storage->host_data()), other_ac.get_pointer(),
+                    other_ac.byte_size());
+        storage->host_written();
+    }
+
+    /// Overwrite the equally-sized `other_buffer` with the contents of the grid.
+    void copy_to_buffer(sycl::buffer<Cell, 2> other_buffer) {
+        if (get_grid_range() != other_buffer.get_range()) {
+            throw std::range_error("The target buffer has not the same size as the grid");
+        }
+        storage->require_host();
+        sycl::host_accessor other_ac(other_buffer, sycl::write_only);
+        std::memcpy(static_cast<void *>(other_ac.get_pointer()), storage->host_data(),
+                    other_ac.byte_size());
+    }
+
+    /**
+     * Host-side window onto the cells. Constructing one waits for outstanding device work on the
+     * grid and brings the host mirror up to date (what a `sycl::host_accessor` does implicitly in
+     * the reference, Grid.hpp:145-153); a writable accessor marks the device copy stale, so the next
+     * update uploads the mirror first.
+     */
+    template <sycl::access::mode access_mode = sycl::access::mode::read_write> class GridAccessor {
+      public:
+        static constexpr int dimensions = 2;
+        static constexpr bool is_read_only = (access_mode == sycl::access::mode::read);
+        using value_type = std::conditional_t<is_read_only, const Cell, Cell>;
+        using reference = value_type &;
+
+        /// Pointer to one row; its subscript selects the column.
+        class Row {
+          public:
+            explicit Row(value_type *row) : row(row) {}
+            reference operator[](std::size_t c) const { return row[c]; }
+
+          private:
+            value_type *row;
+        };
+
+        GridAccessor(Grid &grid) : storage(grid.storage), width(grid.get_grid_width()) {
+            storage->require_host();
+            if constexpr (!is_read_only)
+                storage->host_written();
+            data = storage->host_data();
+        }
+
+        Row operator[](std::size_t r) const { return Row(data + r * width); }
+        reference operator[](sycl::id<2> id) const { return data[id[0] * width + id[1]]; }
+
+        sycl::range<2> get_range() const { return sycl::range<2>(storage->height, storage->width); }
+        value_type *get_pointer() const { return data; }
+        std::size_t size() const { return storage->n_cells(); }
+        std::size_t byte_size() const { return storage->n_cells() * sizeof(Cell); }
+
+      private:
+        std::shared_ptr<internal::GridStorage<Cell>> storage; // keeps `data` alive
+        std::size_t width;
+        value_type *data;
+    };
+
+    /// Number of rows.
+    std::size_t get_grid_height() const { return storage->height; }
+
+    /// Number of columns.
+    std::size_t get_grid_width() const { return storage->width; }
+
+    /// (rows, columns).
+    sycl::range<2> get_grid_range() const { return sycl::range<2>(storage->height, storage->width); }
+
+    /// New, uninitialised grid of the same extent (and on the same device).
+    Grid make_similar() const { return Grid(storage->height, storage->width, storage->device); }
+
+    /// B200 extension: the shared state behind this handle (used by StencilUpdate).
+    internal::GridStorage<Cell> &get_storage() { return *storage; }
+
+  private:
+    using Storage = internal::GridStorage<Cell>;
+    std::shared_ptr<Storage> storage;
+};
+
+} // namespace cuda
+} // namespace stencil

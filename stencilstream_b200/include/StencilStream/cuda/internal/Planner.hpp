@@ -1,0 +1,214 @@
+/*
+ * StencilStream-B200 — launch planning for the fused generation loop.
+ *
+ * Decides, per transition function and device, how many iterations one launch fuses (k), the
+ * shape of the CTA (column groups x row groups) and of its output tile, and the dynamic shared
+ * memory that follows from it. The reference has nothing comparable for its cuda backend (one
+ * work-item per cell, k = 1: StencilStream/cuda/StencilUpdate.hpp:209-215); the closest relative is
+ * the FPGA tiling backend's compile-time tile/temporal-parallelism arithmetic
+ * (StencilStream/tiling/internal/StencilUpdateKernel.hpp:79-99), whose halo rule
+ * `halo = radius * n_subiterations * fused iterations` is the one used here.
+ *
+ * Every choice can be overridden, in this order of precedence: `StencilUpdate::Params` fields
+ * (fused_iterations, tile_rows), then the environment (STST_FUSE, STST_TILE_ROWS, STST_BLOCK_Y,
+ * STST_BLOCK_X, STST_TMA), then the built-in heuristic.
+ */
+#pragma once
+#include "Helpers.hpp"
+#include "Runtime.hpp"
+#include "TileKernel.hpp"
+
+#include <algorithm>
+#include <cstdlib>
+#include <stdexcept>
+#include <string>
+
+namespace stencil {
+namespace cuda {
+namespace internal {
+
+struct LaunchPlan {
+    unsigned fused_iterations; ///< k: iterations per full launch
+    unsigned block_x, block_y; ///< CTA shape; block_x * CW columns are staged per tile row
+    unsigned tile_h, tile_w;   ///< output tile of a full (k-iteration) launch
+    unsigned halo, hpad;       ///< halo depth of a full launch, and its column-aligned version
+    std::size_t smem_bytes;    ///< dynamic shared memory of a full launch
+    bool use_tma;
+};
+
+inline long env_long(const char *name, long fallback) {
+    const char *v = std::getenv(name);
+    return (v && *v) ? std::atol(v) : fallback;
+}
+
+/// Column-group width: 128-bit vectors of the widest plane element, at most 4 columns.
+template <typename Cell> constexpr int column_group_width() {
+    const std::size_t widest = CellLayout<Cell>::max_plane_bytes();
+    if (widest >= 16)
+        return 1;
+    if (widest >= 8)
+        return 2;
+    return 4;
+}
+
+/// Whether every plane of `Cell` can be staged by a TMA box load.
+template <typename Cell> constexpr bool tma_capable() {
+    using L = CellLayout<Cell>;
+    constexpr int cw = column_group_width<Cell>();
+    for (std::size_t i = 0; i < L::n_planes; i++) {
+        const std::size_t b = L::plane_bytes(i);
+        if (!(b == 1 || b == 2 || b == 4 || b == 8))
+            return false;
+        if ((b * cw * 32) % 16 != 0)
+            return false;
+    }
+    return true;
+}
+
+struct TileShape {
+    unsigned halo, hpad, tile_h, tile_w, rows, cols;
+    std::size_t smem_bytes;
+    double efficiency; ///< useful cells / staged cells
+    bool feasible;
+};
+
+/// Geometry of a launch that fuses `k` iterations with the given CTA shape and shared-memory budget.
+template <typename Cell>
+TileShape shape_for(unsigned k, unsigned n_sub, unsigned radius, unsigned cw, unsigned block_x,
+                    unsigned tile_rows_override, std::size_t smem_budget, unsigned grid_h) {
+    TileShape s{};
+    s.halo = k * n_sub * radius;
+    s.hpad = (s.halo + cw - 1) / cw * cw;
+    s.cols = block_x * cw;
+    s.feasible = false;
+    if (2 * s.hpad >= s.cols)
+        return s;
+    s.tile_w = s.cols - 2 * s.hpad;
+    const unsigned n_buffers = (k * n_sub > 1) ? 2 : 1;
+    const std::size_t per_row = tile_buffer_bytes<Cell>(1, s.cols) * n_buffers;
+    // tile_buffer_bytes pads every plane to 128 bytes; leave a little slack for that.
+    const std::size_t usable = smem_budget > 4096 ? smem_budget - 2048 : 0;
+    unsigned max_rows = unsigned(std::min<std::size_t>(usable / std::max<std::size_t>(per_row, 1), 256));
+    if (max_rows <= 2 * s.halo)
+        return s;
+    unsigned tile_h = max_rows - 2 * s.halo;
+    if (tile_rows_override > 0)
+        tile_h = std::min(tile_h, tile_rows_override);
+    tile_h = std::min(tile_h, std::max(grid_h, 1u));
+    s.tile_h = tile_h;
+    s.rows = tile_h + 2 * s.halo;
+    s.smem_bytes = tile_buffer_bytes<Cell>(s.rows, s.cols) * n_buffers;
+    s.efficiency = double(s.tile_h) * s.tile_w / (double(s.rows) * s.cols);
+    s.feasible = s.smem_bytes <= smem_budget;
+    return s;
+}
+
+/**
+ * Plan launches for transition function `F` on `device`.
+ *
+ * The heuristic models the time per cell-iteration of a k-fused launch as
+ *     max(HBM bytes / k, on-chip work) / efficiency
+ * with on-chip work growing with the cell size, and picks the k that minimises it among the
+ * feasible ones (at most `max_k`). Two CTAs per SM are targeted so that one CTA's tile staging
+ * overlaps the other's sweeps.
+ */
+template <typename F>
+LaunchPlan make_plan(int device, unsigned grid_h, unsigned grid_w, std::size_t n_iterations,
+                     unsigned fused_override, unsigned tile_rows_override) {
+    using Cell = typename F::Cell;
+    using L = CellLayout<Cell>;
+    constexpr unsigned cw = unsigned(column_group_width<Cell>());
+    constexpr unsigned n_sub = unsigned(F::n_subiterations);
+    constexpr unsigned radius = unsigned(F::stencil_radius);
+
+    stst_device_info info;
+    STST_RT_CHECK(stst_get_device_info(device, &info));
+    const std::size_t smem_optin = std::size_t(info.max_smem_per_block_optin);
+    const std::size_t smem_sm = std::size_t(info.max_smem_per_sm);
+
+    unsigned block_x = unsigned(env_long("STST_BLOCK_X", 0));
+    if (block_x == 0) {
+        // 256 staged columns for small cells, narrower tiles once a cell is tens of bytes wide.
+        block_x = sizeof(Cell) <= 16 ? 64 : 32;
+        while (block_x > 32 && block_x * cw / 2 >= std::max(grid_w, 1u) + 2 * cw)
+            block_x /= 2;
+    }
+    block_x = std::max(32u, block_x / 32 * 32);
+    unsigned block_y = unsigned(env_long("STST_BLOCK_Y", 0));
+    if (block_y == 0)
+        block_y = std::max(1u, 256u / block_x);
+
+    if (fused_override == 0)
+        fused_override = unsigned(env_long("STST_FUSE", 0));
+    if (tile_rows_override == 0)
+        tile_rows_override = unsigned(env_long("STST_TILE_ROWS", 0));
+    const unsigned ctas_per_sm = unsigned(std::max(1l, env_long("STST_CTAS_PER_SM", 2)));
+
+    const unsigned k_cap = unsigned(
+        std::min<std::size_t>(std::max<std::size_t>(n_iterations, 1), max_fused_iterations));
+
+    // Shared memory available to one CTA if `ctas_per_sm` are to be co-resident (1 KB each is
+    // reserved by the hardware).
+    auto budget_for = [&](unsigned ctas) {
+        std::size_t per_cta = smem_sm / ctas;
+        per_cta = per_cta > 1024 ? per_cta - 1024 : 0;
+        return std::min(per_cta, smem_optin);
+    };
+
+    auto evaluate = [&](unsigned k, unsigned ctas) {
+        return shape_for<Cell>(k, n_sub, radius, cw, block_x, tile_rows_override, budget_for(ctas),
+                               grid_h);
+    };
+
+    unsigned best_k = 0;
+    TileShape best{};
+    if (fused_override > 0) {
+        best_k = std::min(fused_override, k_cap);
+        best = evaluate(best_k, ctas_per_sm);
+        if (!best.feasible)
+            best = evaluate(best_k, 1);
+        if (!best.feasible)
+            throw std::invalid_argument("StencilStream-B200: fused_iterations=" +
+                                        std::to_string(best_k) +
+                                        " does not fit into shared memory for this cell type");
+    } else {
+        // Cost model in "HBM-byte equivalents" per cell-iteration.
+        const double hbm_bytes = 2.0 * double(sizeof(Cell)) * n_sub; // one read + one write / sweep
+        const double onchip = 0.55 * double(sizeof(Cell)) * n_sub + 1.0 * n_sub;
+        double best_cost = 0.0;
+        for (unsigned k = 1; k <= k_cap; k++) {
+            TileShape s = evaluate(k, ctas_per_sm);
+            if (!s.feasible)
+                s = evaluate(k, 1);
+            if (!s.feasible || s.efficiency < 0.35)
+                continue;
+            const double cost = std::max(hbm_bytes / k, onchip) / s.efficiency;
+            if (best_k == 0 || cost < best_cost * 0.97) {
+                best_k = k;
+                best = s;
+                best_cost = cost;
+            }
+        }
+        if (best_k == 0)
+            throw std::invalid_argument(
+                "StencilStream-B200: cell type too large for a shared-memory tile");
+    }
+
+    LaunchPlan plan{};
+    plan.fused_iterations = best_k;
+    plan.block_x = block_x;
+    plan.block_y = block_y;
+    plan.tile_h = best.tile_h;
+    plan.tile_w = best.tile_w;
+    plan.halo = best.halo;
+    plan.hpad = best.hpad;
+    plan.smem_bytes = best.smem_bytes;
+    plan.use_tma = tma_capable<Cell>() && env_long("STST_TMA", 1) != 0 && best.cols <= 256 &&
+                   best.rows <= 256;
+    (void)L::n_planes;
+    return plan;
+}
+
+} // namespace internal
+} // namespace cuda
+} // namespace stencil

@@ -1,0 +1,635 @@
+/*
+ * StencilStream-B200 — the generation loop as sm_100a kernels.
+ *
+ * This file replaces the device side of the reference's cuda backend: `aos_stencil_kernel`
+ * (reference StencilStream/cuda/StencilUpdate.hpp:227-263), `soa_stencil_kernel` (:346-393) and the
+ * `scatter_kernel`/`gather_kernel` pair (:294-321, :408-438). The reference launches one sweep per
+ * (iteration, sub-iteration), one work-item per cell, every work-item gathering its (2r+1)^2
+ * neighbourhood from global memory. Here one launch advances the grid by up to
+ * `max_fused_iterations` iterations:
+ *
+ *   1. A CTA owns an output tile of tile_h x tile_w cells and stages the tile plus a halo of
+ *      d = n_gens * n_subiterations * radius cells (columns padded to the vector width) into shared
+ *      memory, one dense row-major plane per cell field, either with 128-bit cp.async or with one
+ *      TMA box load per plane.
+ *   2. It then runs the n_gens * n_subiterations sweeps entirely in shared memory, ping-ponging
+ *      between two tile buffers; the region that is still exact shrinks by `radius` per sweep
+ *      (overlapped/trapezoidal temporal blocking; the rule is the reference's own for its FPGA
+ *      pipeline: StencilStream/tiling/internal/StencilUpdateKernel.hpp:79-99, :240-254, :314-320).
+ *      Cells outside the global grid are re-set to `halo_value` after every sweep, exactly as the
+ *      reference presents them (cuda/StencilUpdate.hpp:241-252 — the halo is never evolved).
+ *   3. The last sweep writes its CW-wide column groups straight to HBM with 128-bit stores.
+ *
+ * Inside a sweep a thread owns CW adjacent columns and walks down a run of rows, holding the
+ * (2r+1) x (CW+2r) window in registers: per row it issues one vector shared-memory load per plane,
+ * takes the 2r edge columns from its warp neighbours with shuffles, builds the user-visible
+ * `Stencil` objects in registers and calls the transition function CW times. Loads of neighbour
+ * fields the functor never reads are dead code and disappear.
+ *
+ * Tiles whose halo-extended footprint lies completely inside the grid take a path without any
+ * bounds logic; only border tiles pay for halo handling.
+ */
+#pragma once
+#include "../../Stencil.hpp"
+#include "Helpers.hpp"
+
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <cstdint>
+#include <type_traits>
+
+namespace stencil {
+namespace cuda {
+namespace internal {
+
+/// Upper bound for the number of iterations fused into one launch (sizes the TDV parameter array).
+inline constexpr unsigned max_fused_iterations = 16;
+
+/// Geometry of one fused launch; passed by value.
+struct SweepGeometry {
+    unsigned grid_h, grid_w; ///< global grid extent (rows, columns)
+    int buf_row0;            ///< global row held in row 0 of every plane (slab origin, ghosts incl.)
+    int out_row_lo;          ///< first global row this launch has to produce
+    int out_row_hi;          ///< one past the last global row this launch has to produce
+    unsigned tile_h, tile_w; ///< output tile extent
+    unsigned halo;           ///< d = n_gens * n_subiterations * radius
+    unsigned hpad;           ///< column halo, d rounded up to a multiple of CW
+    unsigned n_gens;         ///< iterations fused into this launch (>= 1)
+    unsigned tiles_x;        ///< tiles per tile-row (blockIdx.x = ty * tiles_x + tx)
+    unsigned use_tma;        ///< non-zero: stage tiles with TMA box loads (maps valid)
+    unsigned long long iteration0; ///< global index of the first fused iteration
+};
+
+template <typename TDV> struct TdvArray {
+    TDV v[max_fused_iterations];
+};
+
+/// One 128-byte TMA descriptor per plane (only read when SweepGeometry::use_tma != 0).
+struct alignas(64) TensorMapSet {
+    unsigned char map[max_planes][128];
+};
+
+// ------------------------------------------------------------------------------------------------
+// small device helpers
+// ------------------------------------------------------------------------------------------------
+
+template <typename T, int N> struct alignas((sizeof(T) * N) % 16 == 0 ? 16
+                                            : (sizeof(T) * N) % 8 == 0 ? 8
+                                            : (sizeof(T) * N) % 4 == 0 ? 4
+                                                                       : alignof(T)) Pack {
+    T v[N];
+};
+
+template <typename T>
+inline constexpr bool is_shuffleable_v = std::is_trivially_copyable_v<T> &&
+                                         (sizeof(T) == 1 || sizeof(T) == 2 || sizeof(T) == 4 ||
+                                          sizeof(T) == 8);
+
+#if defined(__CUDACC__)
+
+template <typename To, typename From> __device__ __forceinline__ To bit_cast_dev(From const &f) {
+    static_assert(sizeof(To) >= sizeof(From));
+    To t{};
+    memcpy(&t, &f, sizeof(From));
+    return t;
+}
+
+template <typename T> __device__ __forceinline__ T from_bits(unsigned long long bits) {
+    T t;
+    memcpy(&t, &bits, sizeof(T));
+    return t;
+}
+
+/// Value of `v` held by the lane `delta` below (up) / above (down) the caller.
+template <typename T> __device__ __forceinline__ T shuffle_from_lower_lane(T const &v) {
+    if constexpr (sizeof(T) <= 4) {
+        unsigned bits = bit_cast_dev<unsigned>(v);
+        bits = __shfl_up_sync(0xffffffffu, bits, 1);
+        return from_bits<T>(bits);
+    } else {
+        unsigned long long bits = bit_cast_dev<unsigned long long>(v);
+        bits = __shfl_up_sync(0xffffffffu, bits, 1);
+        return from_bits<T>(bits);
+    }
+}
+
+template <typename T> __device__ __forceinline__ T shuffle_from_upper_lane(T const &v) {
+    if constexpr (sizeof(T) <= 4) {
+        unsigned bits = bit_cast_dev<unsigned>(v);
+        bits = __shfl_down_sync(0xffffffffu, bits, 1);
+        return from_bits<T>(bits);
+    } else {
+        unsigned long long bits = bit_cast_dev<unsigned long long>(v);
+        bits = __shfl_down_sync(0xffffffffu, bits, 1);
+        return from_bits<T>(bits);
+    }
+}
+
+template <int Bytes>
+__device__ __forceinline__ void cp_async_group(void *smem_dst, const void *gmem_src) {
+    unsigned saddr = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+    if constexpr (Bytes % 16 == 0) {
+#pragma unroll
+        for (int o = 0; o < Bytes; o += 16) {
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(saddr + o),
+                         "l"(static_cast<const char *>(gmem_src) + o)
+                         : "memory");
+        }
+    } else if constexpr (Bytes == 8) {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(saddr), "l"(gmem_src)
+                     : "memory");
+    } else {
+        static_assert(Bytes == 4);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(saddr), "l"(gmem_src)
+                     : "memory");
+    }
+}
+
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.wait_all;\n" ::: "memory");
+}
+
+// ---- mbarrier + TMA (cp.async.bulk.tensor) -----------------------------------------------------
+
+__device__ __forceinline__ void mbarrier_init(unsigned long long *bar, unsigned count) {
+    unsigned addr = static_cast<unsigned>(__cvta_generic_to_shared(bar));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(addr), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ void fence_mbarrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+}
+
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+}
+
+__device__ __forceinline__ void mbarrier_arrive_expect_tx(unsigned long long *bar, unsigned bytes) {
+    unsigned addr = static_cast<unsigned>(__cvta_generic_to_shared(bar));
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(addr), "r"(bytes)
+                 : "memory");
+}
+
+__device__ __forceinline__ void mbarrier_wait_parity(unsigned long long *bar, unsigned parity) {
+    unsigned addr = static_cast<unsigned>(__cvta_generic_to_shared(bar));
+    unsigned done = 0;
+    do {
+        asm volatile("{\n"
+                     ".reg .pred p;\n"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+                     "selp.u32 %0, 1, 0, p;\n"
+                     "}\n"
+                     : "=r"(done)
+                     : "r"(addr), "r"(parity)
+                     : "memory");
+    } while (!done);
+}
+
+__device__ __forceinline__ void tma_load_2d(void *smem_dst, const void *tensor_map, int x, int y,
+                                            unsigned long long *bar) {
+    unsigned dst = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+    unsigned mbar = static_cast<unsigned>(__cvta_generic_to_shared(bar));
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+                 " [%0], [%1, {%3, %4}], [%2];\n" ::"r"(dst),
+                 "l"(tensor_map), "r"(mbar), "r"(x), "r"(y)
+                 : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// shared-memory tile bookkeeping
+// ------------------------------------------------------------------------------------------------
+
+/// Bytes of one tile buffer (all planes, each plane padded to 128 bytes).
+template <typename Cell>
+STST_HD inline std::size_t tile_buffer_bytes(unsigned tile_rows, unsigned tile_cols) {
+    using L = CellLayout<Cell>;
+    std::size_t total = 0;
+    for (std::size_t i = 0; i < L::n_planes; i++) {
+        std::size_t b = std::size_t(tile_rows) * tile_cols * L::plane_bytes(i);
+        total += (b + 127) / 128 * 128;
+    }
+    return total;
+}
+
+template <typename Cell> struct TileView {
+    using L = CellLayout<Cell>;
+    unsigned char *base;
+    unsigned rows, cols; // THH, TWH
+    unsigned plane_off[L::n_planes];
+
+    __device__ __forceinline__ TileView(unsigned char *base, unsigned rows, unsigned cols)
+        : base(base), rows(rows), cols(cols) {
+        unsigned off = 0;
+#pragma unroll
+        for (unsigned i = 0; i < L::n_planes; i++) {
+            plane_off[i] = off;
+            unsigned b = rows * cols * unsigned(L::plane_bytes(i));
+            off += (b + 127u) / 128u * 128u;
+        }
+    }
+
+    template <std::size_t I> __device__ __forceinline__ typename L::template plane_t<I> *plane() const {
+        return reinterpret_cast<typename L::template plane_t<I> *>(base + plane_off[I]);
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// tile staging: HBM -> shared memory
+// ------------------------------------------------------------------------------------------------
+
+/**
+ * Fill tile buffer `tile` with the grid cells at global rows [gy0, gy0 + rows) and global columns
+ * [gx0, gx0 + cols); positions outside the global grid receive `halo_value`.
+ * Ends with a CTA-wide barrier.
+ */
+template <typename Cell, int CW, bool kInterior>
+__device__ __forceinline__ void stage_tile(TileView<Cell> const &tile, PlaneSet const &src,
+                                           TensorMapSet const &maps, SweepGeometry const &geo,
+                                           Cell const &halo_value, int gy0, int gx0,
+                                           unsigned long long *mbar) {
+    using L = CellLayout<Cell>;
+    const int c0 = int(threadIdx.x) * CW;
+    const int gx = gx0 + c0;
+
+    if (geo.use_tma) {
+        // One box load per plane, issued by a single thread; out-of-grid elements arrive as zeros
+        // and are patched below (border tiles only).
+        if (threadIdx.x == 0 && threadIdx.y == 0) {
+            unsigned total = 0;
+            for_each_plane<Cell>([&](auto I) {
+                total += tile.rows * tile.cols * unsigned(sizeof(typename L::template plane_t<I>));
+            });
+            mbarrier_arrive_expect_tx(mbar, total);
+            for_each_plane<Cell>([&](auto I) {
+                tma_load_2d(tile.template plane<I>(), &maps.map[I][0], gx0, gy0 - geo.buf_row0,
+                            mbar);
+            });
+        }
+        mbarrier_wait_parity(mbar, 0);
+        if constexpr (!kInterior) {
+            for (int row = int(threadIdx.y); row < int(tile.rows); row += int(blockDim.y)) {
+                const int gy = gy0 + row;
+                const bool row_in = gy >= 0 && gy < int(geo.grid_h);
+                for_each_plane<Cell>([&](auto I) {
+                    auto *s = tile.template plane<I>() + std::size_t(row) * tile.cols + c0;
+#pragma unroll
+                    for (int i = 0; i < CW; i++) {
+                        const bool in = row_in && (gx + i) >= 0 && (gx + i) < int(geo.grid_w);
+                        if (!in)
+                            s[i] = L::template get<I>(halo_value);
+                    }
+                });
+            }
+            __syncthreads();
+        }
+        return;
+    }
+
+    for_each_plane<Cell>([&](auto I) {
+        using T = typename L::template plane_t<I>;
+        T *sp = tile.template plane<I>();
+        const T *gp = static_cast<const T *>(src.base[I]);
+        const unsigned long long pitch = src.pitch[I];
+        for (int row = int(threadIdx.y); row < int(tile.rows); row += int(blockDim.y)) {
+            const int gy = gy0 + row;
+            T *s = sp + std::size_t(row) * tile.cols + c0;
+            const T *g = gp + (long long)(gy - geo.buf_row0) * (long long)pitch + gx;
+            if constexpr (kInterior) {
+                if constexpr ((sizeof(T) * CW) % 16 == 0 || sizeof(T) * CW == 8 ||
+                              sizeof(T) * CW == 4) {
+                    cp_async_group<int(sizeof(T)) * CW>(s, g);
+                } else {
+                    *reinterpret_cast<Pack<T, CW> *>(s) = *reinterpret_cast<const Pack<T, CW> *>(g);
+                }
+            } else {
+                const bool row_in = gy >= 0 && gy < int(geo.grid_h);
+                if (row_in && gx >= 0 && gx + CW <= int(geo.grid_w)) {
+                    *reinterpret_cast<Pack<T, CW> *>(s) = *reinterpret_cast<const Pack<T, CW> *>(g);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < CW; i++) {
+                        const bool in = row_in && (gx + i) >= 0 && (gx + i) < int(geo.grid_w);
+                        s[i] = in ? g[i] : L::template get<I>(halo_value);
+                    }
+                }
+            }
+        }
+    });
+    if constexpr (kInterior)
+        cp_async_wait_all();
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------------
+// one sweep (one sub-iteration) over the still-exact part of a tile
+// ------------------------------------------------------------------------------------------------
+
+/**
+ * Apply sub-iteration `SUB` of `tf` to tile rows [row_lo, row_hi) of `in`, writing either into the
+ * tile buffer `out` or — if `to_global` — into the destination planes in HBM.
+ *
+ * \tparam kRotate Unroll the row loop (2r+1)-fold so that the register window rotates by renaming
+ *                 instead of by moves. Pays off for light functors, bloats code for heavy ones.
+ */
+template <typename F, int CW, bool kInterior, bool kRotate, std::size_t SUB>
+__device__ __forceinline__ void
+sweep_rows(F const &tf, typename F::Cell const &halo_value,
+           typename F::TimeDependentValue const &tdv, std::size_t iteration,
+           TileView<typename F::Cell> const &in, TileView<typename F::Cell> const &out,
+           bool to_global, PlaneSet const &dst, SweepGeometry const &geo, int gy0, int gx0,
+           int row_lo, int row_hi) {
+    using Cell = typename F::Cell;
+    using TDV = typename F::TimeDependentValue;
+    using L = CellLayout<Cell>;
+    using StencilImpl = Stencil<Cell, F::stencil_radius, TDV>;
+    constexpr int R = int(F::stencil_radius);
+    constexpr int D = 2 * R + 1;
+    constexpr int WC = CW + 2 * R;
+    static_assert(R <= CW, "stencil radius must not exceed the per-thread column group width");
+
+    const int cols = int(in.cols);
+    const int c0 = int(threadIdx.x) * CW;
+    const int lane = int(threadIdx.x) & 31;
+
+    // Split the rows of this sweep evenly over the blockDim.y row groups (uniform per warp).
+    const int per_group = (row_hi - row_lo + int(blockDim.y) - 1) / int(blockDim.y);
+    const int y_begin = row_lo + int(threadIdx.y) * per_group;
+    const int y_end = min(y_begin + per_group, row_hi);
+    if (y_begin >= y_end)
+        return;
+
+    Cell win[D][WC];
+
+    // Load tile row `row`, columns [c0 - R, c0 + CW + R), into `w`.
+    auto load_row = [&](Cell(&w)[WC], int row) {
+        for_each_plane<Cell>([&](auto I) {
+            using T = typename L::template plane_t<I>;
+            const T *rp = in.template plane<I>() + row * cols;
+            const Pack<T, CW> p = *reinterpret_cast<const Pack<T, CW> *>(rp + c0);
+#pragma unroll
+            for (int i = 0; i < CW; i++)
+                L::template get<I>(w[R + i]) = p.v[i];
+#pragma unroll
+            for (int j = 1; j <= R; j++) {
+                T left, right;
+                if constexpr (is_shuffleable_v<T>) {
+                    left = shuffle_from_lower_lane(p.v[CW - j]);
+                    right = shuffle_from_upper_lane(p.v[j - 1]);
+                    if (lane == 0)
+                        left = rp[max(c0 - j, 0)];
+                    if (lane == 31)
+                        right = rp[min(c0 + CW - 1 + j, cols - 1)];
+                } else {
+                    left = rp[max(c0 - j, 0)];
+                    right = rp[min(c0 + CW - 1 + j, cols - 1)];
+                }
+                L::template get<I>(w[R - j]) = left;
+                L::template get<I>(w[R + CW - 1 + j]) = right;
+            }
+        });
+    };
+
+    // Compute the CW cells of tile row `y` from the window whose top row sits in slot `top`.
+    auto compute_row = [&](auto top_c, int y) {
+        constexpr int top = decltype(top_c)::value;
+        const int gy = gy0 + y;
+        Cell result[CW];
+#pragma unroll
+        for (int i = 0; i < CW; i++) {
+            const int gx = gx0 + c0 + i;
+            bool in_grid = true;
+            if constexpr (!kInterior) {
+                in_grid = gy >= 0 && gy < int(geo.grid_h) && gx >= 0 && gx < int(geo.grid_w);
+            }
+            if (in_grid) {
+                StencilImpl st(sycl::id<2>(std::size_t(unsigned(gy)), std::size_t(unsigned(gx))),
+                               sycl::range<2>(geo.grid_h, geo.grid_w), iteration, SUB, tdv);
+#pragma unroll
+                for (int sr = 0; sr < D; sr++) {
+#pragma unroll
+                    for (int sc = 0; sc < D; sc++) {
+                        st[sycl::id<2>(sr, sc)] = win[(top + sr) % D][i + sc];
+                    }
+                }
+                result[i] = tf(st);
+            } else {
+                result[i] = halo_value;
+            }
+        }
+
+        if (!to_global) {
+            for_each_plane<Cell>([&](auto I) {
+                using T = typename L::template plane_t<I>;
+                Pack<T, CW> q;
+#pragma unroll
+                for (int i = 0; i < CW; i++)
+                    q.v[i] = L::template get<I>(result[i]);
+                *reinterpret_cast<Pack<T, CW> *>(out.template plane<I>() + y * cols + c0) = q;
+            });
+        } else {
+            // Only the tile's own column groups are exact after the last sweep.
+            const bool own_group = c0 >= int(geo.hpad) && c0 < int(geo.hpad + geo.tile_w);
+            if (!own_group)
+                return;
+            const int gxg = gx0 + c0;
+            if constexpr (!kInterior) {
+                if (gy < geo.out_row_lo || gy >= geo.out_row_hi || gy >= int(geo.grid_h))
+                    return;
+            }
+            for_each_plane<Cell>([&](auto I) {
+                using T = typename L::template plane_t<I>;
+                T *g = static_cast<T *>(dst.base[I]) +
+                       (long long)(gy - geo.buf_row0) * (long long)dst.pitch[I] + gxg;
+                if (kInterior || gxg + CW <= int(geo.grid_w)) {
+                    Pack<T, CW> q;
+#pragma unroll
+                    for (int i = 0; i < CW; i++)
+                        q.v[i] = L::template get<I>(result[i]);
+                    *reinterpret_cast<Pack<T, CW> *>(g) = q;
+                } else {
+#pragma unroll
+                    for (int i = 0; i < CW; i++) {
+                        if (gxg + i < int(geo.grid_w))
+                            g[i] = L::template get<I>(result[i]);
+                    }
+                }
+            });
+        }
+    };
+
+    // Prime the window with the D-1 rows above/around the first row.
+#pragma unroll
+    for (int j = 0; j < D - 1; j++)
+        load_row(win[j], y_begin - R + j);
+
+    if constexpr (kRotate) {
+        for (int y = y_begin; y < y_end; y += D) {
+            [&]<int... Us>(std::integer_sequence<int, Us...>) {
+                (
+                    [&] {
+                        if (y + Us < y_end) {
+                            load_row(win[(Us + D - 1) % D], y + Us + R);
+                            compute_row(std::integral_constant<int, Us>{}, y + Us);
+                        }
+                    }(),
+                    ...);
+            }(std::make_integer_sequence<int, D>{});
+        }
+    } else {
+        for (int y = y_begin; y < y_end; y++) {
+            load_row(win[D - 1], y + R);
+            compute_row(std::integral_constant<int, 0>{}, y);
+#pragma unroll
+            for (int j = 0; j < D - 1; j++) {
+#pragma unroll
+                for (int i = 0; i < WC; i++)
+                    win[j][i] = win[j + 1][i];
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// one tile: stage, run all fused sweeps, write back
+// ------------------------------------------------------------------------------------------------
+
+template <typename F, int CW, bool kInterior, bool kRotate>
+__device__ __forceinline__ void
+run_tile(F const &tf, typename F::Cell const &halo_value,
+         TdvArray<typename F::TimeDependentValue> const &tdvs, PlaneSet const &src,
+         PlaneSet const &dst, TensorMapSet const &maps, SweepGeometry const &geo,
+         unsigned char *smem, unsigned long long *mbar, int gy0, int gx0) {
+    using Cell = typename F::Cell;
+    constexpr int R = int(F::stencil_radius);
+    constexpr unsigned n_sub = unsigned(F::n_subiterations);
+
+    const unsigned rows = geo.tile_h + 2 * geo.halo;
+    const unsigned cols = blockDim.x * CW;
+    const unsigned buffer_bytes = unsigned(tile_buffer_bytes<Cell>(rows, cols));
+
+    TileView<Cell> buf0(smem, rows, cols);
+    TileView<Cell> buf1(smem + buffer_bytes, rows, cols);
+
+    stage_tile<Cell, CW, kInterior>(buf0, src, maps, geo, halo_value, gy0, gx0, mbar);
+
+    unsigned step = 0;
+    for (unsigned g = 0; g < geo.n_gens; g++) {
+        const std::size_t iteration = std::size_t(geo.iteration0) + g;
+        const typename F::TimeDependentValue tdv = tdvs.v[g];
+        [&]<std::size_t... Subs>(std::index_sequence<Subs...>) {
+            (
+                [&] {
+                    const bool last = (g + 1 == geo.n_gens) && (Subs + 1 == n_sub);
+                    const int lo = int(step + 1) * R;
+                    const int hi = int(rows) - int(step + 1) * R;
+                    TileView<Cell> const &in = (step & 1u) ? buf1 : buf0;
+                    TileView<Cell> const &out = (step & 1u) ? buf0 : buf1;
+                    sweep_rows<F, CW, kInterior, kRotate, Subs>(tf, halo_value, tdv, iteration, in,
+                                                                out, last, dst, geo, gy0, gx0, lo,
+                                                                hi);
+                    if (!last)
+                        __syncthreads();
+                    step++;
+                }(),
+                ...);
+        }(std::make_index_sequence<n_sub>{});
+    }
+}
+
+/**
+ * The fused generation-loop kernel. Grid: one CTA per output tile, blockIdx.x = ty * tiles_x + tx;
+ * block: (TWH / CW, row groups), blockDim.x a multiple of 32.
+ * Dynamic shared memory: two tile buffers (one if the launch consists of a single sweep).
+ */
+template <typename F, int CW, bool kRotate, int kMaxThreads, int kMinBlocks>
+__global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
+    fused_sweep_kernel(const __grid_constant__ F tf,
+                       const __grid_constant__ typename F::Cell halo_value,
+                       const __grid_constant__ TdvArray<typename F::TimeDependentValue> tdvs,
+                       const __grid_constant__ PlaneSet src, const __grid_constant__ PlaneSet dst,
+                       const __grid_constant__ TensorMapSet maps,
+                       const __grid_constant__ SweepGeometry geo) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ unsigned long long mbar;
+
+    if (geo.use_tma) {
+        if (threadIdx.x == 0 && threadIdx.y == 0) {
+            mbarrier_init(&mbar, 1);
+            fence_mbarrier_init();
+        }
+        __syncthreads();
+    }
+
+    const unsigned tx = blockIdx.x % geo.tiles_x;
+    const unsigned ty = blockIdx.x / geo.tiles_x;
+    const int tile_gy = geo.out_row_lo + int(ty * geo.tile_h);
+    const int tile_gx = int(tx * geo.tile_w);
+    const int gy0 = tile_gy - int(geo.halo);
+    const int gx0 = tile_gx - int(geo.hpad);
+
+    const bool interior = gy0 >= 0 && tile_gy + int(geo.tile_h + geo.halo) <= int(geo.grid_h) &&
+                          tile_gy + int(geo.tile_h) <= geo.out_row_hi && gx0 >= 0 &&
+                          tile_gx + int(geo.tile_w + geo.hpad) <= int(geo.grid_w);
+
+    if (interior) {
+        run_tile<F, CW, true, kRotate>(tf, halo_value, tdvs, src, dst, maps, geo, smem, &mbar, gy0,
+                                       gx0);
+    } else {
+        run_tile<F, CW, false, false>(tf, halo_value, tdvs, src, dst, maps, geo, smem, &mbar, gy0,
+                                      gx0);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host <-> device layout conversion (array-of-structs staging <-> planes)
+// ------------------------------------------------------------------------------------------------
+
+/**
+ * Spread `n_rows` x `width` cells, stored as a dense row-major array of whole cells at `aos`, over the
+ * planes, starting at plane row `plane_row0`. Counterpart of the reference's `scatter_kernel`
+ * (cuda/StencilUpdate.hpp:294-321), but run once per host->device transfer instead of once per update.
+ */
+template <typename Cell>
+__global__ void __launch_bounds__(256)
+    scatter_cells_kernel(const Cell *__restrict__ aos, PlaneSet planes, unsigned long long width,
+                         unsigned long long plane_row0, unsigned long long n_cells) {
+    using L = CellLayout<Cell>;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long idx = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+         idx < n_cells; idx += stride) {
+        const unsigned long long r = idx / width, c = idx - r * width;
+        const Cell cell = aos[idx];
+        for_each_plane<Cell>([&](auto I) {
+            using T = typename L::template plane_t<I>;
+            static_cast<T *>(planes.base[I])[(plane_row0 + r) * planes.pitch[I] + c] =
+                L::template get<I>(cell);
+        });
+    }
+}
+
+/// Inverse of scatter_cells_kernel; counterpart of the reference's `gather_kernel` (:408-438).
+template <typename Cell>
+__global__ void __launch_bounds__(256)
+    gather_cells_kernel(Cell *__restrict__ aos, PlaneSet planes, unsigned long long width,
+                        unsigned long long plane_row0, unsigned long long n_cells) {
+    using L = CellLayout<Cell>;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long idx = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+         idx < n_cells; idx += stride) {
+        const unsigned long long r = idx / width, c = idx - r * width;
+        Cell cell;
+        for_each_plane<Cell>([&](auto I) {
+            using T = typename L::template plane_t<I>;
+            L::template get<I>(cell) =
+                static_cast<const T *>(planes.base[I])[(plane_row0 + r) * planes.pitch[I] + c];
+        });
+        aos[idx] = cell;
+    }
+}
+
+#endif // __CUDACC__
+
+} // namespace internal
+} // namespace cuda
+} // namespace stencil
