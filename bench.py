@@ -1,0 +1,446 @@
+#!/usr/bin/env python
+"""Benchmark of the StencilStream-B200 generation loop.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload jacobi5|hotspot] [--rows R --cols C --iterations I]
+
+Metric (BASELINE.json / reference scripts/benchmark-common.jl:97-98): GCell-updates/s =
+rows * cols * n_iterations / time, one "update" being one full iteration (all sub-iterations).
+A *step* is one `StencilUpdate` call advancing the whole synthetic grid by `--iterations`
+iterations. Default workload at N=1: BASELINE.json configs[1], Jacobi 5-point fp32 16384x16384,
+1000 generations, input as the reference generates it (examples/jacobi/jacobi.cpp:111-124).
+
+`value`        grid resident in HBM before the timed region; K steps timed with CUDA events on the
+               stream the kernels are launched on, barrier + synchronize on both sides, max over ranks.
+`e2e`          the same step through the public Grid/StencilUpdate API starting from cells in pinned
+               host memory (GridAccessor image): upload + update + download inside the timed region.
+`roofline`     HBM roofline of the fused sweep kernel: algorithmic bytes (2*sizeof(Cell)*n_sub per
+               cell-iteration, the reference's own model) per launch / mean launch duration, against
+               the measured copy bandwidth in MEASURED_PEAKS.json.
+`cpu_baseline` the CPU oracle (reference-built if available) timed on this box's host cores on a
+               bounded sample of the same workload (rank 0, N=1 only).
+`--impl reference` times the reference's CPU implementation instead (same metric/config keys).
+
+Multi-GPU (torchrun, one rank per GPU): the grid is row-sharded, every rank owns `rows` rows (weak
+scaling) and exchanges halo rows with its neighbours once per fused launch.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+WORKLOAD_LABEL = {
+    "jacobi5": "Jacobi 5-point fp32 {rows}x{cols}, {iters} generations (BASELINE.json configs[1])",
+    "hotspot": "Rodinia HotSpot fp32 temp+power {rows}x{cols}, {iters} generations (BASELINE.json configs[2])",
+}
+DTYPE = {"jacobi5": "f32", "hotspot": "f32", "fdtd": "f32", "convection_pt": "f64", "conway": "u8"}
+
+
+# ---------------------------------------------------------------------------------------------------
+# workload set-up
+# ---------------------------------------------------------------------------------------------------
+
+def make_workload(name: str, rows: int, cols: int):
+    """(params struct, halo cell, function filling an array view with the synthetic input)."""
+    from stencilstream_b200 import workloads as W
+
+    if name == "jacobi5":
+        return W.jacobi5_params(), 0.0, lambda view, r0, r1, total: fill_jacobi(view, r0, r1, total, cols)
+    if name == "hotspot":
+        return W.hotspot_params(rows, cols), (0.0, 0.0), \
+            lambda view, r0, r1, total: fill_hotspot(view, r0, r1, total, cols)
+    raise SystemExit(f"bench.py: unsupported workload {name!r}")
+
+
+def fill_jacobi(view, r0, r1, total_rows, cols):
+    """Rows [r0, r1) of the centred unit square of a total_rows x cols grid (jacobi.cpp:111-124)."""
+    r = np.arange(r0, r1, dtype=np.float64)[:, None]
+    c = np.arange(cols, dtype=np.float64)[None, :]
+    inside = (r >= total_rows * 0.25) & (r < total_rows * 0.75) & (c >= cols * 0.25) & (c < cols * 0.75)
+    view[...] = inside.astype(np.float32)
+
+
+def fill_hotspot(view, r0, r1, total_rows, cols):
+    """Rows [r0, r1) of the reference's synthetic HotSpot input (data/input_gen.jl:3-15)."""
+    view["temp"] = np.float32(30.0)
+    view["power"] = np.float32(0.0)
+    r_lo, r_hi = total_rows // 4, (3 * total_rows) // 4
+    c_lo, c_hi = cols // 4, (3 * cols) // 4
+    lo = max(r_lo - 1, r0)
+    hi = min(r_hi, r1)
+    if hi > lo:
+        view["power"][lo - r0:hi - r0, max(c_lo - 1, 0):c_hi] = np.float32(0.5)
+
+
+# ---------------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------------
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons of one GPU every 100 ms while the timed region runs."""
+
+    REASONS = {
+        0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
+        0x4: "sw_power_cap", 0x80: "hw_power_brake", 0x2: "applications_clocks_setting",
+    }
+
+    def __init__(self, device_index: int):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            self._handle = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self._handle, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self._nvml = None
+
+    def _loop(self):
+        nv = self._nvml
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self._handle, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._handle)
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        if self._nvml is not None:
+            self._thread = threading.Thread(target=self._loop, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# device-side timing on the runtime's stream
+# ---------------------------------------------------------------------------------------------------
+
+class StreamTimer:
+    """CUDA events recorded on the stream StencilStream-B200 launches its kernels on."""
+
+    def __init__(self, device: int):
+        from stencilstream_b200 import _native
+        self.rt = _native.runtime_lib()
+        self.stream = C.c_void_p()
+        self._check(self.rt.stst_default_stream(device, C.byref(self.stream)))
+        self.start, self.stop = C.c_void_p(), C.c_void_p()
+        self._check(self.rt.stst_event_create(1, C.byref(self.start)))
+        self._check(self.rt.stst_event_create(1, C.byref(self.stop)))
+
+    def _check(self, status):
+        if status != 0:
+            raise RuntimeError(self.rt.stst_last_error().decode())
+
+    def sync(self):
+        self._check(self.rt.stst_stream_synchronize(self.stream))
+
+    def begin(self):
+        self._check(self.rt.stst_event_record(self.start, self.stream))
+
+    def end_ms(self) -> float:
+        self._check(self.rt.stst_event_record(self.stop, self.stream))
+        self._check(self.rt.stst_event_synchronize(self.stop))
+        ms = C.c_float()
+        self._check(self.rt.stst_event_elapsed_ms(self.start, self.stop, C.byref(ms)))
+        return float(ms.value)
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU baseline / reference arm
+# ---------------------------------------------------------------------------------------------------
+
+def time_cpu_oracle(workload: str, rows: int, cols: int, target_seconds: float = 12.0):
+    """Time the CPU oracle (reference-built cpu backend if present, else the C port) on a bounded
+    sample: a `sample_rows` x cols slab of the workload for `iters` iterations, sized from a short
+    calibration run so that it takes roughly `target_seconds`."""
+    import oracle
+
+    impl = oracle.best()
+    cores = os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    params, halo, fill = make_workload(workload, rows, cols)
+    from stencilstream_b200 import _native
+    dtype = _native.CELL_DTYPES[workload]
+    sample_rows = min(rows, 2048)
+    cells = np.empty((sample_rows, cols), dtype=dtype)
+    fill(cells, 0, sample_rows, sample_rows)
+
+    t0 = time.perf_counter()
+    impl.run(workload, params, halo, cells, 0, 1)
+    per_iter = time.perf_counter() - t0
+    iters = int(max(2, min(200, target_seconds / max(per_iter, 1e-3))))
+    t0 = time.perf_counter()
+    impl.run(workload, params, halo, cells, 0, iters)
+    elapsed = time.perf_counter() - t0
+    value = sample_rows * cols * iters / elapsed / 1e9
+    return {
+        "value": value, "unit": "GCell-updates/s", "cores": cores,
+        "kind": "reference" if impl.kind == "reference" else "port",
+        "sample": f"{sample_rows}x{cols} slab of the workload grid, {iters} iterations, "
+                  f"{elapsed:.1f} s on {cores} host threads (OpenMP over rows)",
+    }, elapsed
+
+
+def run_reference_arm(args, rank: int, world: int):
+    if rank != 0:
+        return
+    rows, cols, iters = args.rows, args.cols, args.iterations
+    total_steps = args.steps + args.warmup
+    budget = 150.0 / max(total_steps, 1)
+    results = []
+    baseline = None
+    for i in range(total_steps):
+        baseline, elapsed = time_cpu_oracle(args.workload, rows, cols, target_seconds=min(budget, 15.0))
+        if i >= args.warmup:
+            results.append((baseline["value"], elapsed))
+    value = float(np.mean([v for v, _ in results]))
+    ms = float(np.mean([e for _, e in results]) * 1e3)
+    baseline["value"] = value
+    line = {
+        "impl": "reference", "metric": "GCell-updates/s", "value": value, "unit": "GCell-updates/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": DTYPE.get(args.workload, "f32"), "data": "synthetic",
+        "config": {"workload": WORKLOAD_LABEL[args.workload].format(rows=rows, cols=cols, iters=iters),
+                   "note": "reference StencilStream cpu backend on host cores; each step is a bounded "
+                           "sample of the workload (see cpu_baseline.sample)"},
+        "cpu_baseline": baseline,
+        "e2e": {"value": value, "unit": "GCell-updates/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------
+
+def measured_peak_gbs():
+    path = ROOT / "MEASURED_PEAKS.json"
+    if path.exists():
+        try:
+            return float(json.loads(path.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def run_ours(args, rank: int, world: int, local_rank: int):
+    from stencilstream_b200 import Grid, Params, StencilUpdate, workload_info
+    from stencilstream_b200 import _native
+
+    device = local_rank
+    os.environ["STST_DEVICE"] = str(device)
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist_mod
+        torch.cuda.set_device(device)
+        dist_mod.init_process_group("nccl", device_id=torch.device("cuda", device))
+        dist = dist_mod
+
+    rows, cols, iters = args.rows, args.cols, args.iterations
+    workload = args.workload
+    info = workload_info(workload)
+    params, halo, fill = make_workload(workload, rows * world, cols)
+    dtype = _native.CELL_DTYPES[workload]
+
+    if world > 1:
+        from stencilstream_b200.sharding import ShardedRun
+        runner = ShardedRun(workload, params, halo, rows, cols, rank, world, device, dist,
+                            fused_iterations=args.fuse)
+    else:
+        runner = None
+
+    timer = StreamTimer(device)
+
+    def barrier():
+        timer.sync()
+        if dist is not None:
+            dist.barrier()
+            import torch
+            torch.cuda.synchronize()
+
+    # ---- resident-data measurement ------------------------------------------------------------------
+    if runner is None:
+        grid = Grid(workload, rows, cols, device=device)
+        view = grid.accessor("write")
+        fill(view, 0, rows, rows)
+        del view
+        grid.sync_to_device()
+        update = StencilUpdate(workload, Params(transition_function=params, halo_value=halo,
+                                                n_iterations=iters, blocking=False,
+                                                fused_iterations=args.fuse))
+
+        def step():
+            return update(grid)
+    else:
+        runner.fill(fill)
+
+        def step():
+            return runner.step(iters)
+
+    for _ in range(args.warmup):
+        out = step()
+    barrier()
+    launches_before = update.get_n_launches() if runner is None else runner.n_launches
+    with ClockSampler(device) as clocks:
+        timer.begin()
+        for _ in range(args.steps):
+            out = step()
+        elapsed_ms = timer.end_ms()
+        barrier()
+    launches = (update.get_n_launches() if runner is None else runner.n_launches) - launches_before
+    del out
+
+    if dist is not None:
+        import torch
+        t = torch.tensor([elapsed_ms], dtype=torch.float64, device=f"cuda:{device}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+
+    total_cells = rows * world * cols
+    ms_per_step = elapsed_ms / args.steps
+    value = total_cells * iters / (ms_per_step * 1e-3) / 1e9
+
+    stats = update.get_stats() if runner is None else runner.stats()
+    k = int(stats.fused_iterations)
+
+    # ---- roofline of the fused sweep kernel -----------------------------------------------------------
+    peak, peak_source = measured_peak_gbs()
+    launches_per_step = launches / args.steps
+    # One launch advances this rank's rows*cols cells by (iters / launches_per_step) iterations on average.
+    bytes_per_launch = info.bytes_per_cell_iteration * rows * cols * iters / launches_per_step
+    launch_ms = ms_per_step / launches_per_step
+    achieved = bytes_per_launch / (launch_ms * 1e-3) / 1e9
+    roofline = {
+        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "traffic": None, "peak_source": peak_source,
+        "kernel": "fused_sweep_kernel", "fused_iterations": k,
+        "algorithmic_bytes_per_cell_iteration": int(info.bytes_per_cell_iteration),
+        "note": "effective fraction: k fused iterations cross HBM once, so it may exceed the physical "
+                "DRAM fraction (see profiles/ for dram__bytes)",
+    }
+
+    # ---- end-to-end through the public API, host buffers in pinned memory -----------------------------
+    e2e = None
+    if runner is None:
+        host_grid = Grid(workload, rows, cols, device=device)
+        e2e_update = StencilUpdate(workload, Params(transition_function=params, halo_value=halo,
+                                                    n_iterations=iters, blocking=True,
+                                                    fused_iterations=args.fuse))
+        e2e_steps = max(1, min(args.steps, 3))
+        times = []
+        for i in range(1 + e2e_steps):
+            view = host_grid.accessor("write")      # pinned host image; marks the device copy stale
+            if i == 0:
+                fill(view, 0, rows, rows)
+            del view
+            timer.sync()
+            t0 = time.perf_counter()
+            result = e2e_update(host_grid)          # H2D upload + layout + all fused launches
+            checksum = float(result.accessor("read")[rows // 2, cols // 2]["temp"]
+                             if dtype.names else result.accessor("read")[rows // 2, cols // 2])  # D2H
+            t1 = time.perf_counter()
+            if i > 0:
+                times.append(t1 - t0)
+            del result
+        e2e_value = total_cells * iters / float(np.mean(times)) / 1e9
+        e2e = {"value": e2e_value, "unit": "GCell-updates/s",
+               "h2d_bytes_per_step": int(rows * cols * dtype.itemsize),
+               "d2h_bytes_per_step": int(rows * cols * dtype.itemsize),
+               "ms_per_step": float(np.mean(times) * 1e3), "checksum": checksum}
+        del host_grid
+    else:
+        e2e = runner.e2e(fill, iters, timer)
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_baseline, _ = time_cpu_oracle(workload, rows, cols)
+
+    if rank == 0:
+        line = {
+            "metric": "GCell-updates/s", "value": value, "unit": "GCell-updates/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": DTYPE.get(workload, "f32"), "data": "synthetic",
+            "config": {
+                "workload": WORKLOAD_LABEL[workload].format(rows=rows * world, cols=cols, iters=iters),
+                "rows_per_gpu": rows, "cols": cols, "iterations_per_step": iters,
+                "parallelism": f"row-sharded x{world}" if world > 1 else "single GPU",
+                "l2": "grid (>= 1 GiB per buffer) exceeds the 126 MB L2; no flush needed",
+                "fused_iterations": k, "tile": [int(stats.tile_h), int(stats.tile_w)],
+                "block": [int(stats.block_x), int(stats.block_y)], "tma": bool(stats.use_tma),
+                "smem_bytes": int(stats.smem_bytes),
+            },
+            "roofline": roofline,
+            "pct_of_hbm_roofline_8TBps": 100.0 * value * info.bytes_per_cell_iteration / world / 8000.0,
+            "cpu_baseline": cpu_baseline,
+            "e2e": e2e,
+            "gpu_launches": int(launches),
+            "clocks": clocks.summary(),
+        }
+        print(json.dumps(line), flush=True)
+
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="jacobi5", choices=sorted(WORKLOAD_LABEL))
+    ap.add_argument("--rows", type=int, default=16384, help="rows per GPU")
+    ap.add_argument("--cols", type=int, default=16384)
+    ap.add_argument("--iterations", type=int, default=1000, help="iterations per step")
+    ap.add_argument("--fuse", type=int, default=0, help="fused iterations per launch (0 = planner)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus != world and world > 1:
+        args.gpus = world
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -159,6 +159,13 @@ int stst_grid_copy_from_host(stst_grid *grid, const void *cells, size_t bytes);
 int stst_grid_copy_to_host(stst_grid *grid, void *cells, size_t bytes);
 /* Force the device copy to be current (uploads a pending host image); for resident-data timing. */
 int stst_grid_sync_to_device(stst_grid *grid);
+/*
+ * GridAccessor<mode> (Grid.hpp:145-153): waits for pending device work, brings the pinned host image
+ * up to date and returns a pointer to it (rows*cols cells, row-major), valid while any handle to the
+ * cells exists. mode: 0 = read, 1 = write, 2 = read_write; writable modes mark the device copy stale,
+ * so the next update uploads the image first.
+ */
+int stst_grid_host_accessor(stst_grid *grid, int mode, void **cells);
 
 /* ---- updaters ------------------------------------------------------------------------------------ */
 

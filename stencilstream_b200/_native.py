@@ -152,7 +152,7 @@ WORKLOADS_SYMBOLS = [
     "stst_workloads_abi_version", "stst_workloads_last_error", "stst_workload_count",
     "stst_workload_name", "stst_workload_get_info", "stst_grid_create", "stst_grid_share",
     "stst_grid_make_similar", "stst_grid_destroy", "stst_grid_shape", "stst_grid_copy_from_host",
-    "stst_grid_copy_to_host", "stst_grid_sync_to_device", "stst_update_create",
+    "stst_grid_copy_to_host", "stst_grid_sync_to_device", "stst_grid_host_accessor", "stst_update_create",
     "stst_update_set_params", "stst_update_apply", "stst_update_get_stats", "stst_update_destroy",
 ]
 
@@ -198,6 +198,7 @@ def workloads_lib(strict: bool | None = None):
         lib.stst_grid_copy_from_host.argtypes = [vp, vp, C.c_size_t]
         lib.stst_grid_copy_to_host.argtypes = [vp, vp, C.c_size_t]
         lib.stst_grid_sync_to_device.argtypes = [vp]
+        lib.stst_grid_host_accessor.argtypes = [vp, C.c_int, C.POINTER(vp)]
         lib.stst_update_create.argtypes = [C.c_char_p, C.POINTER(UpdateParams), C.POINTER(vp)]
         lib.stst_update_set_params.argtypes = [vp, C.POINTER(UpdateParams)]
         lib.stst_update_apply.argtypes = [vp, vp, C.POINTER(vp)]

@@ -56,6 +56,14 @@ def workload_info(workload: str, strict: bool | None = None) -> WorkloadInfo:
     return info
 
 
+class _OwnedView(np.ndarray):
+    """ndarray view that keeps the owning Grid (and with it the pinned memory) alive."""
+    _owner = None
+
+    def __array_finalize__(self, obj):
+        self._owner = getattr(obj, "_owner", None)
+
+
 class Grid:
     """A two-dimensional grid of cells resident in B200 HBM (mirror of `stencil::cuda::Grid<Cell>`).
 
@@ -128,6 +136,23 @@ class Grid:
             raise ValueError("copy_to_buffer needs a writable C-contiguous array")
         _check(self._lib, self._lib.stst_grid_copy_to_host(
             self._handle, buffer.ctypes.data_as(C.c_void_p), buffer.nbytes))
+
+    def accessor(self, mode: str = "read_write") -> np.ndarray:
+        """Mirror of `Grid::GridAccessor<mode>` (reference Grid.hpp:145-153): a 2-D numpy view of the
+        grid's pinned host image. Waits for device work on the grid; writable modes make the next
+        update upload the image. The view keeps this grid object alive."""
+        code = {"read": 0, "write": 1, "read_write": 2}[mode]
+        ptr = C.c_void_p()
+        _check(self._lib, self._lib.stst_grid_host_accessor(self._handle, code, C.byref(ptr)))
+        rows, cols = self.get_grid_range()
+        n_bytes = rows * cols * self.dtype.itemsize
+        raw = (C.c_ubyte * max(n_bytes, 1)).from_address(ptr.value)
+        view = np.frombuffer(raw, dtype=self.dtype, count=rows * cols).reshape(rows, cols)
+        view = view.view(_OwnedView)
+        view._owner = self
+        if code == 0:
+            view.flags.writeable = False
+        return view
 
     # -- conveniences -------------------------------------------------------------------------------
     def to_numpy(self) -> np.ndarray:

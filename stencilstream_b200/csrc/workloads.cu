@@ -40,6 +40,7 @@ struct GridBase {
     virtual void copy_from_host(const void *cells) = 0;
     virtual void copy_to_host(void *cells) = 0;
     virtual void sync_to_device() = 0;
+    virtual void *host_accessor(int mode) = 0;
     virtual GridBase *share() = 0;
     virtual GridBase *make_similar() = 0;
 };
@@ -62,6 +63,14 @@ template <typename Cell> struct GridHolder final : GridBase {
     void sync_to_device() override {
         grid.get_storage().require_device();
         sc::internal::check(stst_stream_synchronize(grid.get_storage().stream), "stream sync");
+    }
+    void *host_accessor(int mode) override {
+        if (mode == 0) {
+            typename sc::Grid<Cell>::template GridAccessor<sycl::access::mode::read> ac(grid);
+            return const_cast<void *>(static_cast<const void *>(ac.get_pointer()));
+        }
+        typename sc::Grid<Cell>::template GridAccessor<sycl::access::mode::read_write> ac(grid);
+        return static_cast<void *>(ac.get_pointer());
     }
     GridBase *share() override { return new GridHolder(workload, grid); }
     GridBase *make_similar() override { return new GridHolder(workload, grid.make_similar()); }
@@ -306,6 +315,15 @@ STST_EXPORT int stst_grid_sync_to_device(stst_grid *grid) {
         return report(STST_ERR_INVALID_ARGUMENT, "null argument");
     return guarded([&] {
         grid->impl->sync_to_device();
+        return STST_OK;
+    });
+}
+
+STST_EXPORT int stst_grid_host_accessor(stst_grid *grid, int mode, void **cells) {
+    if (!grid || !cells || mode < 0 || mode > 2)
+        return report(STST_ERR_INVALID_ARGUMENT, "bad argument");
+    return guarded([&] {
+        *cells = grid->impl->host_accessor(mode);
         return STST_OK;
     });
 }

@@ -35,6 +35,8 @@
 #include "internal/TileKernel.hpp"
 
 #include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <memory>
 #include <vector>
 
@@ -164,12 +166,25 @@ template <concepts::TransitionFunction F, bool split_cell_structure = false> cla
         if (grid_h == 0 || grid_w == 0)
             return swap_grid_a;
 
+        const bool trace = std::getenv("STST_TRACE") != nullptr;
+        auto t_begin = std::chrono::high_resolution_clock::now();
+        auto lap = [&](const char *what) {
+            if (!trace)
+                return;
+            auto now = std::chrono::high_resolution_clock::now();
+            std::fprintf(stderr, "[stst] %-22s %9.3f ms\n", what,
+                         std::chrono::duration<double, std::milli>(now - t_begin).count());
+            t_begin = now;
+        };
+
         source.require_device();
+        lap("require_device");
 
         const internal::LaunchPlan plan = internal::make_plan<F>(
             source.device, grid_h, grid_w, params.n_iterations, params.fused_iterations,
             params.tile_rows);
         last_plan = plan;
+        lap("make_plan");
 
         const std::size_t k = plan.fused_iterations;
         const std::size_t n_full = params.n_iterations / k;
@@ -179,6 +194,7 @@ template <concepts::TransitionFunction F, bool split_cell_structure = false> cla
         GridImpl swap_grid_b = (launches > 1) ? source_grid.make_similar() : swap_grid_a;
         swap_grid_a.get_storage().allocate_device();
         swap_grid_b.get_storage().allocate_device();
+        lap("allocate scratch grids");
 
         GridImpl *pass_source = &source_grid;
         GridImpl *pass_target = &swap_grid_a;
@@ -195,6 +211,7 @@ template <concepts::TransitionFunction F, bool split_cell_structure = false> cla
             }
         }
         pass_source->get_storage().device_written();
+        lap("submit launches");
         return *pass_source;
     }
 

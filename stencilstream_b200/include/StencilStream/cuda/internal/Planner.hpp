@@ -41,6 +41,21 @@ inline long env_long(const char *name, long fallback) {
     return (v && *v) ? std::atol(v) : fallback;
 }
 
+/// Static properties of a device, queried once (cudaGetDeviceProperties takes milliseconds and can
+/// stall behind queued work, which is far too slow for a per-call query).
+inline const stst_device_info &cached_device_info(int device) {
+    constexpr int max_devices = 64;
+    static stst_device_info infos[max_devices];
+    static bool valid[max_devices] = {};
+    if (device < 0 || device >= max_devices)
+        throw std::invalid_argument("StencilStream-B200: device ordinal out of range");
+    if (!valid[device]) {
+        STST_RT_CHECK(stst_get_device_info(device, &infos[device]));
+        valid[device] = true;
+    }
+    return infos[device];
+}
+
 /// Column-group width: 128-bit vectors of the widest plane element, at most 4 columns.
 template <typename Cell> constexpr int column_group_width() {
     const std::size_t widest = CellLayout<Cell>::max_plane_bytes();
@@ -65,6 +80,24 @@ template <typename Cell> constexpr bool tma_capable() {
     return true;
 }
 
+/**
+ * Granularity (in columns) of the column halo and hence of every tile's first column. It is a
+ * multiple of the column-group width; with TMA staging the byte offset of a box's first column must
+ * additionally be a multiple of 16 in EVERY plane (cp.async.bulk.tensor traps otherwise), which for
+ * 1- and 2-byte elements is coarser than the column group.
+ */
+template <typename Cell> constexpr unsigned column_alignment(bool for_tma) {
+    using L = CellLayout<Cell>;
+    unsigned align = unsigned(column_group_width<Cell>());
+    if (for_tma) {
+        for (std::size_t i = 0; i < L::n_planes; i++) {
+            const unsigned need = unsigned(16 / (L::plane_bytes(i) < 16 ? L::plane_bytes(i) : 16));
+            align = need > align ? need : align;
+        }
+    }
+    return align;
+}
+
 struct TileShape {
     unsigned halo, hpad, tile_h, tile_w, rows, cols;
     std::size_t smem_bytes;
@@ -74,11 +107,12 @@ struct TileShape {
 
 /// Geometry of a launch that fuses `k` iterations with the given CTA shape and shared-memory budget.
 template <typename Cell>
-TileShape shape_for(unsigned k, unsigned n_sub, unsigned radius, unsigned cw, unsigned block_x,
-                    unsigned tile_rows_override, std::size_t smem_budget, unsigned grid_h) {
+TileShape shape_for(unsigned k, unsigned n_sub, unsigned radius, unsigned cw, unsigned col_align,
+                    unsigned block_x, unsigned tile_rows_override, std::size_t smem_budget,
+                    unsigned grid_h) {
     TileShape s{};
     s.halo = k * n_sub * radius;
-    s.hpad = (s.halo + cw - 1) / cw * cw;
+    s.hpad = (s.halo + col_align - 1) / col_align * col_align;
     s.cols = block_x * cw;
     s.feasible = false;
     if (2 * s.hpad >= s.cols)
@@ -121,8 +155,7 @@ LaunchPlan make_plan(int device, unsigned grid_h, unsigned grid_w, std::size_t n
     constexpr unsigned n_sub = unsigned(F::n_subiterations);
     constexpr unsigned radius = unsigned(F::stencil_radius);
 
-    stst_device_info info;
-    STST_RT_CHECK(stst_get_device_info(device, &info));
+    const stst_device_info &info = cached_device_info(device);
     const std::size_t smem_optin = std::size_t(info.max_smem_per_block_optin);
     const std::size_t smem_sm = std::size_t(info.max_smem_per_sm);
 
@@ -155,9 +188,12 @@ LaunchPlan make_plan(int device, unsigned grid_h, unsigned grid_w, std::size_t n
         return std::min(per_cta, smem_optin);
     };
 
+    const bool want_tma = tma_capable<Cell>() && env_long("STST_TMA", 1) != 0;
+    const unsigned col_align = column_alignment<Cell>(want_tma);
+
     auto evaluate = [&](unsigned k, unsigned ctas) {
-        return shape_for<Cell>(k, n_sub, radius, cw, block_x, tile_rows_override, budget_for(ctas),
-                               grid_h);
+        return shape_for<Cell>(k, n_sub, radius, cw, col_align, block_x, tile_rows_override,
+                               budget_for(ctas), grid_h);
     };
 
     unsigned best_k = 0;
@@ -203,8 +239,7 @@ LaunchPlan make_plan(int device, unsigned grid_h, unsigned grid_w, std::size_t n
     plan.halo = best.halo;
     plan.hpad = best.hpad;
     plan.smem_bytes = best.smem_bytes;
-    plan.use_tma = tma_capable<Cell>() && env_long("STST_TMA", 1) != 0 && best.cols <= 256 &&
-                   best.rows <= 256;
+    plan.use_tma = want_tma && best.cols <= 256 && best.rows <= 256;
     (void)L::n_planes;
     return plan;
 }
