@@ -147,11 +147,15 @@ class ClockSampler:
 class StreamTimer:
     """CUDA events recorded on the stream StencilStream-B200 launches its kernels on."""
 
-    def __init__(self, device: int):
+    def __init__(self, device: int, record=None, sync=None):
+        """`record(event)` / `sync()` override where events are recorded (default: the runtime's
+        per-device stream, on which single-GPU updates run; slabs record behind both their streams)."""
         from stencilstream_b200 import _native
         self.rt = _native.runtime_lib()
         self.stream = C.c_void_p()
         self._check(self.rt.stst_default_stream(device, C.byref(self.stream)))
+        self._record = record or (lambda ev: self._check(self.rt.stst_event_record(ev, self.stream)))
+        self._sync = sync or (lambda: self._check(self.rt.stst_stream_synchronize(self.stream)))
         self.start, self.stop = C.c_void_p(), C.c_void_p()
         self._check(self.rt.stst_event_create(1, C.byref(self.start)))
         self._check(self.rt.stst_event_create(1, C.byref(self.stop)))
@@ -161,13 +165,13 @@ class StreamTimer:
             raise RuntimeError(self.rt.stst_last_error().decode())
 
     def sync(self):
-        self._check(self.rt.stst_stream_synchronize(self.stream))
+        self._sync()
 
     def begin(self):
-        self._check(self.rt.stst_event_record(self.start, self.stream))
+        self._record(self.start)
 
     def end_ms(self) -> float:
-        self._check(self.rt.stst_event_record(self.stop, self.stream))
+        self._record(self.stop)
         self._check(self.rt.stst_event_synchronize(self.stop))
         ms = C.c_float()
         self._check(self.rt.stst_event_elapsed_ms(self.start, self.stop, C.byref(ms)))
@@ -275,14 +279,17 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     params, halo, fill = make_workload(workload, rows * world, cols)
     dtype = _native.CELL_DTYPES[workload]
 
+    runner = None
     if world > 1:
-        from stencilstream_b200.sharding import ShardedRun
-        runner = ShardedRun(workload, params, halo, rows, cols, rank, world, device, dist,
-                            fused_iterations=args.fuse)
+        from stencilstream_b200.sharding import ShardedStencilUpdate
+        runner = ShardedStencilUpdate(
+            workload, Params(transition_function=params, halo_value=halo, n_iterations=iters,
+                             blocking=False, fused_iterations=args.fuse),
+            rows * world, cols, rank=rank, world=world, device=device, comm=dist,
+            overlap=not args.no_overlap)
+        timer = StreamTimer(device, record=runner.slab.record_event, sync=runner.synchronize)
     else:
-        runner = None
-
-    timer = StreamTimer(device)
+        timer = StreamTimer(device)
 
     def barrier():
         timer.sync()
@@ -290,6 +297,15 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             dist.barrier()
             import torch
             torch.cuda.synchronize()
+
+    def pinned_cells(n_rows):
+        """A numpy view of pinned host memory for n_rows x cols cells."""
+        ptr = C.c_void_p()
+        n_bytes = n_rows * cols * dtype.itemsize
+        if timer.rt.stst_malloc_host(n_bytes, C.byref(ptr)) != 0:
+            raise RuntimeError(timer.rt.stst_last_error().decode())
+        raw = (C.c_ubyte * n_bytes).from_address(ptr.value)
+        return np.frombuffer(raw, dtype=dtype, count=n_rows * cols).reshape(n_rows, cols)
 
     # ---- resident-data measurement ------------------------------------------------------------------
     if runner is None:
@@ -304,23 +320,32 @@ def run_ours(args, rank: int, world: int, local_rank: int):
 
         def step():
             return update(grid)
+
+        def n_launches():
+            return update.get_n_launches()
     else:
-        runner.fill(fill)
+        host_in = pinned_cells(rows)
+        fill(host_in, runner.row_lo, runner.row_hi, rows * world)
+        runner.load(host_in)
+        runner.synchronize()
 
         def step():
-            return runner.step(iters)
+            return runner()
+
+        def n_launches():
+            return runner.get_n_launches()
 
     for _ in range(args.warmup):
         out = step()
     barrier()
-    launches_before = update.get_n_launches() if runner is None else runner.n_launches
+    launches_before = n_launches()
     with ClockSampler(device) as clocks:
         timer.begin()
         for _ in range(args.steps):
             out = step()
         elapsed_ms = timer.end_ms()
         barrier()
-    launches = (update.get_n_launches() if runner is None else runner.n_launches) - launches_before
+    launches = n_launches() - launches_before
     del out
 
     if dist is not None:
@@ -333,12 +358,13 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     ms_per_step = elapsed_ms / args.steps
     value = total_cells * iters / (ms_per_step * 1e-3) / 1e9
 
-    stats = update.get_stats() if runner is None else runner.stats()
+    stats = update.get_stats() if runner is None else runner.info()
     k = int(stats.fused_iterations)
 
     # ---- roofline of the fused sweep kernel -----------------------------------------------------------
     peak, peak_source = measured_peak_gbs()
-    launches_per_step = launches / args.steps
+    # One pass (all launches that together advance the rank's rows by <= k iterations) per k iterations.
+    launches_per_step = -(-iters // k)
     # One launch advances this rank's rows*cols cells by (iters / launches_per_step) iterations on average.
     bytes_per_launch = info.bytes_per_cell_iteration * rows * cols * iters / launches_per_step
     launch_ms = ms_per_step / launches_per_step
@@ -382,7 +408,30 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                "ms_per_step": float(np.mean(times) * 1e3), "checksum": checksum}
         del host_grid
     else:
-        e2e = runner.e2e(fill, iters, timer)
+        # Per rank: owned rows from pinned host memory -> slab (H2D + layout + halo exchange), the
+        # update, owned rows back into pinned host memory. Wall clock between barriers, max over ranks.
+        host_out = pinned_cells(rows)
+        runner.get_params().blocking = True
+        e2e_steps = max(1, min(args.steps, 3))
+        times = []
+        for i in range(1 + e2e_steps):
+            barrier()
+            t0 = time.perf_counter()
+            runner.load(host_in)
+            runner()
+            runner.to_numpy(host_out)
+            t1 = time.perf_counter()
+            import torch
+            t = torch.tensor([t1 - t0], dtype=torch.float64, device=f"cuda:{device}")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            if i > 0:
+                times.append(float(t.item()))
+        mid = host_out[rows // 2, cols // 2]
+        checksum = float(mid["temp"] if dtype.names else mid)
+        e2e = {"value": total_cells * iters / float(np.mean(times)) / 1e9, "unit": "GCell-updates/s",
+               "h2d_bytes_per_step": int(rows * cols * dtype.itemsize) * world,
+               "d2h_bytes_per_step": int(rows * cols * dtype.itemsize) * world,
+               "ms_per_step": float(np.mean(times) * 1e3), "checksum": checksum}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -428,6 +477,8 @@ def main():
     ap.add_argument("--iterations", type=int, default=1000, help="iterations per step")
     ap.add_argument("--fuse", type=int, default=0, help="fused iterations per launch (0 = planner)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true",
+                    help="multi-GPU: one launch per pass instead of boundary-first scheduling")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))

@@ -66,8 +66,11 @@ int stst_free(int device, void *ptr, stst_stream_t stream);
 /* Classic, IPC-exportable allocation (cudaMalloc). */
 int stst_malloc_ipc(int device, size_t bytes, void **ptr);
 int stst_free_ipc(int device, void *ptr);
-int stst_malloc_host(size_t bytes, void **ptr); /* pinned, portable */
+/* Pinned, portable host memory. Freed blocks are cached by size (STST_PINNED_CACHE_MB, default
+ * 16384) because pinning gigabytes costs hundreds of milliseconds; stst_host_cache_trim releases them. */
+int stst_malloc_host(size_t bytes, void **ptr);
 int stst_free_host(void *ptr);
+int stst_host_cache_trim(void);
 int stst_host_register(void *ptr, size_t bytes); /* pin caller-owned memory */
 int stst_host_unregister(void *ptr);
 int stst_memset_async(void *ptr, int value, size_t bytes, stst_stream_t stream);
@@ -95,6 +98,14 @@ int stst_event_record(stst_event_t event, stst_stream_t stream);
 int stst_event_synchronize(stst_event_t event);
 int stst_event_elapsed_ms(stst_event_t start, stst_event_t stop, float *ms);
 int stst_device_synchronize(int device);
+/*
+ * Stream-ordered 32-bit flags in device memory (cuStreamWriteValue32 / cuStreamWaitValue32 with
+ * CU_STREAM_WAIT_VALUE_GEQ). `device_ptr` may be a peer- or IPC-mapped address for writes; waits
+ * poll memory of the stream's own device. Used by the slab partitioner to order halo pushes between
+ * GPUs (and between processes) without host synchronisation.
+ */
+int stst_stream_write_value32(stst_stream_t stream, void *device_ptr, uint32_t value);
+int stst_stream_wait_value32_geq(stst_stream_t stream, void *device_ptr, uint32_t value);
 
 /* --- TMA ------------------------------------------------------------------------------------- */
 /*

@@ -202,6 +202,59 @@ int stst_update_apply(stst_update *update, stst_grid *source, stst_grid **result
 int stst_update_get_stats(stst_update *update, stst_update_stats *stats);
 int stst_update_destroy(stst_update *update);
 
+/* ---- row slabs: the multi-GPU partitioner --------------------------------------------------------
+ *
+ * No counterpart in the reference (its cuda backend drives one device,
+ * StencilStream/cuda/StencilUpdate.hpp:83): a grid of grid_rows x grid_cols cells is cut into
+ * contiguous row slabs, one per GPU, each slab object owning rows [row_lo, row_hi) plus
+ * k * n_subiterations * radius ghost rows per side. Every fused launch stores the rows its
+ * neighbours need directly into their ghost rows over NVLink (peer/IPC-mapped memory) and the slabs
+ * order themselves with stream-ordered flags, so a run needs no host synchronisation and no
+ * collective. The result equals the single-grid update of the whole grid.
+ *
+ * Protocol, identical on every slab of a grid (one slab per process, or several in one process):
+ *   create -> exchange handles (get_ipc_handle/attach_ipc across processes, attach_local within one)
+ *   -> copy_from_host -> exchange_halos -> update ... update -> copy_to_host.
+ * exchange_halos and update are collective in the sense that every slab must issue the same sequence.
+ */
+
+typedef struct stst_slab stst_slab;
+
+typedef struct stst_slab_info {
+    size_t grid_rows, grid_cols, row_lo, row_hi;
+    size_t ghost_rows;   /* k * n_subiterations * radius                         */
+    size_t device_bytes; /* size of the slab's single device allocation          */
+    size_t n_launches;   /* fused kernel launches so far                         */
+    size_t epoch;        /* passes so far (incl. the two an exchange_halos adds) */
+    int device;
+    unsigned fused_iterations, tile_h, tile_w, block_x, block_y, use_tma, overlap;
+    size_t smem_bytes;
+} stst_slab_info;
+
+/* fused_iterations: upper bound for k (0 = automatic); all slabs of a grid must end up with the same
+ * k (compare stst_slab_info.fused_iterations and re-create with the minimum if they differ).
+ * overlap != 0: boundary rows first on a high-priority stream, interior concurrently. */
+int stst_slab_create(const char *workload, size_t grid_rows, size_t grid_cols, size_t row_lo,
+                     size_t row_hi, int device, unsigned fused_iterations, unsigned tile_rows,
+                     int overlap, stst_slab **slab);
+int stst_slab_destroy(stst_slab *slab);
+int stst_slab_get_info(stst_slab *slab, stst_slab_info *info);
+/* side: 0 = the slab above (lower row indices), 1 = the slab below. */
+int stst_slab_get_ipc_handle(stst_slab *slab, unsigned char handle[64]);
+int stst_slab_attach_ipc(stst_slab *slab, int side, const unsigned char handle[64],
+                         size_t peer_row_lo, size_t peer_row_hi);
+int stst_slab_attach_local(stst_slab *slab, int side, stst_slab *peer);
+/* Owned rows only: bytes must equal (row_hi-row_lo)*grid_cols*cell_bytes, else STST_ERR_RANGE.
+ * copy_from_host is asynchronous when `cells` is pinned (stst_malloc_host / stst_host_register). */
+int stst_slab_copy_from_host(stst_slab *slab, const void *cells, size_t bytes);
+int stst_slab_copy_to_host(stst_slab *slab, void *cells, size_t bytes);
+int stst_slab_exchange_halos(stst_slab *slab);
+/* Uses transition_function, halo_value, iteration_offset, n_iterations and blocking of `params`. */
+int stst_slab_update(stst_slab *slab, const stst_update_params *params);
+int stst_slab_synchronize(stst_slab *slab);
+/* The stream a CUDA event must be recorded on to bracket the slab's work (after join). */
+int stst_slab_record_event(stst_slab *slab, void *event);
+
 #ifdef __cplusplus
 }
 #endif

@@ -32,6 +32,10 @@ class Oracle:
         self.lib.oracle_last_error.restype = C.c_char_p
         self.lib.oracle_kind.restype = C.c_char_p
         self.kind = self.lib.oracle_kind().decode()
+        if hasattr(self.lib, "oracle_run_window"):
+            self.lib.oracle_run_window.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                   C.c_void_p] + [C.c_size_t] * 6
+            self.lib.oracle_run_window.restype = C.c_int
 
     def run(self, workload: str, params, halo, cells: np.ndarray, iteration_offset: int,
             n_iterations: int) -> np.ndarray:
@@ -52,6 +56,30 @@ class Oracle:
             raise RuntimeError(f"oracle_run({workload}) failed: "
                                f"{self.lib.oracle_last_error().decode()}")
         return out
+
+
+def _run_window(self, workload: str, params, halo, cells: np.ndarray, row0: int, global_rows: int,
+                iteration_offset: int, n_iterations: int) -> np.ndarray:
+    """`Oracle.run` on rows [row0, row0 + len(cells)) of a grid with `global_rows` rows (C port
+    only): global coordinates, `halo` outside the window. See oracle_run_window in stencil_oracle.c."""
+    cells = np.ascontiguousarray(cells)
+    out = np.empty_like(cells)
+    halo_arr = None
+    if halo is not None:
+        halo_arr = np.zeros((), dtype=cells.dtype)
+        halo_arr[()] = halo
+    status = self.lib.oracle_run_window(
+        workload.encode(), C.addressof(params) if params is not None else None,
+        halo_arr.ctypes.data if halo_arr is not None else None, cells.ctypes.data, out.ctypes.data,
+        cells.shape[0], cells.shape[1], int(row0), int(global_rows), int(iteration_offset),
+        int(n_iterations))
+    if status != 0:
+        raise RuntimeError(f"oracle_run_window({workload}) failed: "
+                           f"{self.lib.oracle_last_error().decode()}")
+    return out
+
+
+Oracle.run_window = _run_window
 
 
 def build(verbose: bool = False) -> None:

@@ -338,15 +338,17 @@ const char *oracle_last_error(void) { return g_error; }
 const char *oracle_kind(void) { return "port"; }
 
 /* One sweep: reference StencilStream/cpu/StencilUpdate.hpp:199-221. */
+/* `rows` x `cols` cells are held; they are rows [row0, row0 + rows) of a grid of `global_rows` rows
+ * (row0 = 0, global_rows = rows for a whole grid). */
 static void sweep(const workload_def *w, const void *params, const unsigned char *halo,
                   const unsigned char *src, unsigned char *dst, size_t rows, size_t cols,
-                  size_t i_iter, size_t i_subiter) {
+                  size_t row0, size_t global_rows, size_t i_iter, size_t i_subiter) {
     const int radius = w->radius;
     const size_t cb = w->cell_bytes;
     stencil_view proto;
     memset(&proto, 0, sizeof(proto));
     proto.radius = radius;
-    proto.grid_range[0] = rows;
+    proto.grid_range[0] = global_rows;
     proto.grid_range[1] = cols;
     proto.iteration = i_iter;
     proto.subiteration = i_subiter;
@@ -357,7 +359,7 @@ static void sweep(const workload_def *w, const void *params, const unsigned char
     for (long long r = 0; r < (long long)rows; r++) {
         stencil_view st = proto;
         for (size_t c = 0; c < cols; c++) {
-            st.id[0] = (size_t)r;
+            st.id[0] = row0 + (size_t)r;
             st.id[1] = c;
             for (int rel_r = 0; rel_r < 2 * radius + 1; rel_r++) {
                 for (int rel_c = 0; rel_c < 2 * radius + 1; rel_c++) {
@@ -383,9 +385,9 @@ static void sweep(const workload_def *w, const void *params, const unsigned char
  * halo: one cell, or NULL for an all-zero cell. Returns 0 on success.
  * Loop order and ping-pong: reference StencilStream/cpu/StencilUpdate.hpp:110-129.
  */
-int oracle_run(const char *workload, const void *params, const void *halo, const void *cells_in,
-               void *cells_out, size_t rows, size_t cols, size_t iteration_offset,
-               size_t n_iterations) {
+static int run_rows(const char *workload, const void *params, const void *halo,
+                    const void *cells_in, void *cells_out, size_t rows, size_t cols, size_t row0,
+                    size_t global_rows, size_t iteration_offset, size_t n_iterations) {
     const workload_def *w = NULL;
     for (size_t i = 0; i < sizeof(workloads) / sizeof(workloads[0]); i++)
         if (strcmp(workloads[i].name, workload) == 0)
@@ -416,7 +418,8 @@ int oracle_run(const char *workload, const void *params, const void *halo, const
     unsigned char *dst = b;
     for (size_t i_iter = 0; i_iter < n_iterations; i_iter++) {
         for (size_t i_sub = 0; i_sub < (size_t)w->n_subiterations; i_sub++) {
-            sweep(w, params, halo_cell, src, dst, rows, cols, iteration_offset + i_iter, i_sub);
+            sweep(w, params, halo_cell, src, dst, rows, cols, row0, global_rows,
+                  iteration_offset + i_iter, i_sub);
             if (i_iter == 0 && i_sub == 0) {
                 src = b;
                 dst = a;
@@ -431,4 +434,30 @@ int oracle_run(const char *workload, const void *params, const void *halo, const
     free(a);
     free(b);
     return 0;
+}
+
+int oracle_run(const char *workload, const void *params, const void *halo, const void *cells_in,
+               void *cells_out, size_t rows, size_t cols, size_t iteration_offset,
+               size_t n_iterations) {
+    return run_rows(workload, params, halo, cells_in, cells_out, rows, cols, 0, rows,
+                    iteration_offset, n_iterations);
+}
+
+/*
+ * The same loop on a WINDOW of a larger grid: `rows` x `cols` cells that are the rows
+ * [row0, row0 + rows) of a grid with `global_rows` rows. Transition functions see global
+ * coordinates and the global extent; cells outside the window read as `halo`, which is wrong for
+ * window-edge rows that have in-grid neighbours outside the window — after n iterations only rows
+ * further than n * n_subiterations * radius from such an edge are exact. Used by the CPU stand-in
+ * for a GPU slab (tests/fake_slab.py) to check the partitioner's halo-depth arithmetic.
+ */
+int oracle_run_window(const char *workload, const void *params, const void *halo,
+                      const void *cells_in, void *cells_out, size_t rows, size_t cols, size_t row0,
+                      size_t global_rows, size_t iteration_offset, size_t n_iterations) {
+    if (row0 + rows > global_rows) {
+        g_error = "window exceeds the grid";
+        return -2;
+    }
+    return run_rows(workload, params, halo, cells_in, cells_out, rows, cols, row0, global_rows,
+                    iteration_offset, n_iterations);
 }

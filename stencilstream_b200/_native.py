@@ -136,12 +136,12 @@ PARAM_TYPES = {
 RT_SYMBOLS = [
     "stst_rt_abi_version", "stst_last_error", "stst_device_count", "stst_get_device_info",
     "stst_set_device", "stst_malloc", "stst_free", "stst_malloc_ipc", "stst_free_ipc",
-    "stst_malloc_host", "stst_free_host", "stst_host_register", "stst_host_unregister",
+    "stst_malloc_host", "stst_free_host", "stst_host_cache_trim", "stst_host_register", "stst_host_unregister",
     "stst_memset_async", "stst_memcpy_h2d_async", "stst_memcpy_d2h_async", "stst_memcpy_d2d_async",
     "stst_memcpy_2d_async", "stst_memcpy_peer_async", "stst_default_stream", "stst_stream_create",
     "stst_stream_destroy", "stst_stream_synchronize", "stst_stream_wait_event", "stst_event_create",
     "stst_event_destroy", "stst_event_record", "stst_event_synchronize", "stst_event_elapsed_ms",
-    "stst_device_synchronize", "stst_tensor_map_encode_2d", "stst_peer_can_access",
+    "stst_device_synchronize", "stst_stream_write_value32", "stst_stream_wait_value32_geq", "stst_tensor_map_encode_2d", "stst_peer_can_access",
     "stst_peer_enable", "stst_ipc_get_mem_handle", "stst_ipc_open_mem_handle",
     "stst_ipc_close_mem_handle", "stst_ipc_get_event_handle", "stst_ipc_open_event_handle",
     "stst_event_create_ipc", "stst_nccl_available", "stst_nccl_get_unique_id",
@@ -154,6 +154,10 @@ WORKLOADS_SYMBOLS = [
     "stst_grid_make_similar", "stst_grid_destroy", "stst_grid_shape", "stst_grid_copy_from_host",
     "stst_grid_copy_to_host", "stst_grid_sync_to_device", "stst_grid_host_accessor", "stst_update_create",
     "stst_update_set_params", "stst_update_apply", "stst_update_get_stats", "stst_update_destroy",
+    "stst_slab_create", "stst_slab_destroy", "stst_slab_get_info", "stst_slab_get_ipc_handle",
+    "stst_slab_attach_ipc", "stst_slab_attach_local", "stst_slab_copy_from_host",
+    "stst_slab_copy_to_host", "stst_slab_exchange_halos", "stst_slab_update", "stst_slab_synchronize",
+    "stst_slab_record_event",
 ]
 
 _libs: dict = {}

@@ -13,9 +13,12 @@
 #include <dlfcn.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 namespace {
@@ -223,17 +226,81 @@ int stst_free_ipc(int device, void *ptr) {
     return 0;
 }
 
+// Pinned host blocks are expensive to create (cudaHostAlloc of 1 GiB takes hundreds of
+// milliseconds), and every result grid that host code looks at needs one. Freed blocks are therefore
+// kept, keyed by their exact size, up to STST_PINNED_CACHE_MB (default 16384) in total.
+namespace {
+std::mutex g_pinned_mutex;
+std::multimap<size_t, void *> g_pinned_free;
+std::unordered_map<void *, size_t> g_pinned_size;
+size_t g_pinned_cached_bytes = 0;
+
+size_t pinned_cache_limit() {
+    static const size_t limit = [] {
+        const char *env = std::getenv("STST_PINNED_CACHE_MB");
+        const size_t mb = (env && *env) ? size_t(std::strtoull(env, nullptr, 10)) : size_t(16384);
+        return mb << 20;
+    }();
+    return limit;
+}
+} // namespace
+
 int stst_malloc_host(size_t bytes, void **ptr) {
     if (!ptr)
         return fail(-1, "stst_malloc_host", "null argument");
-    STST_CUDA(cudaHostAlloc(ptr, bytes == 0 ? 64 : bytes, cudaHostAllocPortable));
+    if (bytes == 0)
+        bytes = 64;
+    {
+        std::lock_guard<std::mutex> lock(g_pinned_mutex);
+        auto it = g_pinned_free.find(bytes);
+        if (it != g_pinned_free.end()) {
+            *ptr = it->second;
+            g_pinned_free.erase(it);
+            g_pinned_cached_bytes -= bytes;
+            return 0;
+        }
+    }
+    cudaError_t err = cudaHostAlloc(ptr, bytes, cudaHostAllocPortable);
+    if (err != cudaSuccess) {
+        // Out of pinnable memory: drop the cache and retry once.
+        (void)cudaGetLastError();
+        (void)stst_host_cache_trim();
+        STST_CUDA(cudaHostAlloc(ptr, bytes, cudaHostAllocPortable));
+    }
+    std::lock_guard<std::mutex> lock(g_pinned_mutex);
+    g_pinned_size[*ptr] = bytes;
     return 0;
 }
 
 int stst_free_host(void *ptr) {
     if (!ptr)
         return 0;
+    {
+        std::lock_guard<std::mutex> lock(g_pinned_mutex);
+        auto it = g_pinned_size.find(ptr);
+        if (it != g_pinned_size.end() && g_pinned_cached_bytes + it->second <= pinned_cache_limit()) {
+            g_pinned_free.emplace(it->second, ptr);
+            g_pinned_cached_bytes += it->second;
+            return 0;
+        }
+        if (it != g_pinned_size.end())
+            g_pinned_size.erase(it);
+    }
     STST_CUDA(cudaFreeHost(ptr));
+    return 0;
+}
+
+int stst_host_cache_trim(void) {
+    std::multimap<size_t, void *> blocks;
+    {
+        std::lock_guard<std::mutex> lock(g_pinned_mutex);
+        blocks.swap(g_pinned_free);
+        g_pinned_cached_bytes = 0;
+        for (auto const &b : blocks)
+            g_pinned_size.erase(b.second);
+    }
+    for (auto const &b : blocks)
+        (void)cudaFreeHost(b.second);
     return 0;
 }
 
@@ -380,6 +447,51 @@ int stst_device_synchronize(int device) {
     STST_CUDA(guard.enter(device));
     STST_CUDA(cudaDeviceSynchronize());
     return 0;
+}
+
+// ---- stream-ordered flags (cuStreamWriteValue32 / cuStreamWaitValue32) ----------------------------
+namespace {
+using StreamValueFn = CUresult (*)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+StreamValueFn g_write_value32 = nullptr, g_wait_value32 = nullptr;
+
+int load_stream_value_ops() {
+    if (g_write_value32 && g_wait_value32)
+        return 0;
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    STST_CUDA(cudaGetDriverEntryPoint("cuStreamWriteValue32", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess)
+        return fail(-1, "stst_stream_write_value32", "cuStreamWriteValue32 unavailable");
+    g_write_value32 = reinterpret_cast<StreamValueFn>(fn);
+    fn = nullptr;
+    STST_CUDA(cudaGetDriverEntryPoint("cuStreamWaitValue32", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess)
+        return fail(-1, "stst_stream_wait_value32_geq", "cuStreamWaitValue32 unavailable");
+    g_wait_value32 = reinterpret_cast<StreamValueFn>(fn);
+    return 0;
+}
+
+int driver_fail(const char *what, CUresult res) {
+    return fail(int(res), what, ("CUDA driver error " + std::to_string(int(res))).c_str());
+}
+} // namespace
+
+int stst_stream_write_value32(stst_stream_t stream, void *device_ptr, uint32_t value) {
+    if (int rc = load_stream_value_ops())
+        return rc;
+    CUresult res = g_write_value32(static_cast<CUstream>(stream),
+                                   reinterpret_cast<CUdeviceptr>(device_ptr), value,
+                                   CU_STREAM_WRITE_VALUE_DEFAULT);
+    return res == CUDA_SUCCESS ? 0 : driver_fail("cuStreamWriteValue32", res);
+}
+
+int stst_stream_wait_value32_geq(stst_stream_t stream, void *device_ptr, uint32_t value) {
+    if (int rc = load_stream_value_ops())
+        return rc;
+    CUresult res = g_wait_value32(static_cast<CUstream>(stream),
+                                  reinterpret_cast<CUdeviceptr>(device_ptr), value,
+                                  CU_STREAM_WAIT_VALUE_GEQ);
+    return res == CUDA_SUCCESS ? 0 : driver_fail("cuStreamWaitValue32", res);
 }
 
 int stst_tensor_map_encode_2d(void *tensor_map_out, const void *base, int elem_bytes,

@@ -7,6 +7,7 @@
  * computes cells on the host.
  */
 #include <StencilStream/cuda/StencilUpdate.hpp>
+#include <StencilStream/cuda/internal/SlabUpdate.hpp>
 #include <stst_workloads.h>
 
 #include "workloads/functors.hpp"
@@ -141,11 +142,87 @@ template <typename F, typename ParamBlock> struct UpdateHolder final : UpdateBas
     }
 };
 
+struct SlabBase {
+    virtual ~SlabBase() = default;
+    const char *workload = nullptr;
+    std::vector<void *> ipc_mappings;
+    virtual std::size_t cell_bytes() const = 0;
+    virtual void info(stst_slab_info &out) = 0;
+    virtual void *device_base() = 0;
+    virtual int device() const = 0;
+    virtual void attach(int side, void *mapped, std::size_t lo, std::size_t hi) = 0;
+    virtual void upload(const void *cells) = 0;
+    virtual void download(void *cells) = 0;
+    virtual void exchange() = 0;
+    virtual void update(const stst_update_params &p) = 0;
+    virtual void synchronize() = 0;
+    virtual void record(void *event) = 0;
+};
+
+template <typename F, typename ParamBlock> struct SlabHolder final : SlabBase {
+    using Slab = sc::internal::SlabUpdate<F>;
+    using Cell = typename F::Cell;
+    std::unique_ptr<Slab> slab;
+
+    SlabHolder(const char *name, typename Slab::Config const &cfg)
+        : slab(std::make_unique<Slab>(cfg)) {
+        workload = name;
+    }
+    ~SlabHolder() override {
+        slab.reset();
+        for (void *m : ipc_mappings)
+            (void)stst_ipc_close_mem_handle(m);
+    }
+    std::size_t cell_bytes() const override { return sizeof(Cell); }
+    void info(stst_slab_info &out) override {
+        std::memset(&out, 0, sizeof(out));
+        auto const &cfg = slab->get_config();
+        auto const &plan = slab->get_plan();
+        out.grid_rows = cfg.grid_rows;
+        out.grid_cols = cfg.grid_cols;
+        out.row_lo = cfg.row_lo;
+        out.row_hi = cfg.row_hi;
+        out.ghost_rows = slab->ghost_rows();
+        out.device_bytes = slab->device_bytes();
+        out.n_launches = slab->get_n_launches();
+        out.epoch = slab->get_epoch();
+        out.device = cfg.device;
+        out.fused_iterations = plan.fused_iterations;
+        out.tile_h = plan.tile_h;
+        out.tile_w = plan.tile_w;
+        out.block_x = plan.block_x;
+        out.block_y = plan.block_y;
+        out.use_tma = plan.use_tma ? 1u : 0u;
+        out.overlap = cfg.overlap ? 1u : 0u;
+        out.smem_bytes = plan.smem_bytes;
+    }
+    void *device_base() override { return slab->device_base(); }
+    int device() const override { return slab->get_config().device; }
+    void attach(int side, void *mapped, std::size_t lo, std::size_t hi) override {
+        slab->attach(side == 0 ? sc::internal::SlabSide::up : sc::internal::SlabSide::down, mapped,
+                     lo, hi);
+    }
+    void upload(const void *cells) override { slab->upload(static_cast<const Cell *>(cells)); }
+    void download(void *cells) override { slab->download(static_cast<Cell *>(cells)); }
+    void exchange() override { slab->exchange_halos(); }
+    void update(const stst_update_params &p) override {
+        auto params = UpdateHolder<F, ParamBlock>::convert(p);
+        slab->run(params.transition_function, params.halo_value, params.iteration_offset,
+                  params.n_iterations);
+        if (params.blocking)
+            slab->synchronize();
+    }
+    void synchronize() override { slab->synchronize(); }
+    void record(void *event) override { slab->record(event); }
+};
+
 struct WorkloadEntry {
     const char *name;
     stst_workload_info info;
     GridBase *(*make_grid)(const char *, std::size_t, std::size_t, int);
     UpdateBase *(*make_update)(const char *, const stst_update_params &);
+    SlabBase *(*make_slab)(const char *, std::size_t, std::size_t, std::size_t, std::size_t, int,
+                           unsigned, unsigned, bool);
 };
 
 template <typename F, typename ParamBlock> WorkloadEntry make_entry(const char *name) {
@@ -165,6 +242,15 @@ template <typename F, typename ParamBlock> WorkloadEntry make_entry(const char *
     };
     e.make_update = [](const char *n, const stst_update_params &p) -> UpdateBase * {
         return new UpdateHolder<F, ParamBlock>(n, p);
+    };
+    e.make_slab = [](const char *n, std::size_t grid_rows, std::size_t grid_cols, std::size_t row_lo,
+                     std::size_t row_hi, int device, unsigned fused, unsigned tile_rows,
+                     bool overlap) -> SlabBase * {
+        if (device < 0)
+            device = sc::internal::default_device_ordinal();
+        typename sc::internal::SlabUpdate<F>::Config cfg{grid_rows, grid_cols, row_lo, row_hi,
+                                                          device,    fused,     tile_rows, overlap};
+        return new SlabHolder<F, ParamBlock>(n, cfg);
     };
     return e;
 }
@@ -216,6 +302,9 @@ struct stst_grid {
 };
 struct stst_update {
     std::unique_ptr<UpdateBase> impl;
+};
+struct stst_slab {
+    std::unique_ptr<SlabBase> impl;
 };
 
 #define STST_EXPORT extern "C" __attribute__((visibility("default")))
@@ -372,4 +461,147 @@ STST_EXPORT int stst_update_get_stats(stst_update *update, stst_update_stats *st
 STST_EXPORT int stst_update_destroy(stst_update *update) {
     delete update;
     return STST_OK;
+}
+
+
+// ---- row slabs ---------------------------------------------------------------------------------------
+
+STST_EXPORT int stst_slab_create(const char *workload, size_t grid_rows, size_t grid_cols,
+                                 size_t row_lo, size_t row_hi, int device,
+                                 unsigned fused_iterations, unsigned tile_rows, int overlap,
+                                 stst_slab **slab) {
+    const WorkloadEntry *e = find(workload);
+    if (!e)
+        return report(STST_ERR_UNKNOWN_WORKLOAD, std::string("unknown workload: ") +
+                                                     (workload ? workload : "(null)"));
+    if (!slab)
+        return report(STST_ERR_INVALID_ARGUMENT, "slab is null");
+    if (row_hi <= row_lo || row_hi > grid_rows || grid_cols == 0)
+        return report(STST_ERR_INVALID_ARGUMENT, "illegal slab row range");
+    return guarded([&] {
+        *slab = new stst_slab{std::unique_ptr<SlabBase>(
+            e->make_slab(e->name, grid_rows, grid_cols, row_lo, row_hi, device, fused_iterations,
+                         tile_rows, overlap != 0))};
+        return STST_OK;
+    });
+}
+
+STST_EXPORT int stst_slab_destroy(stst_slab *slab) {
+    delete slab;
+    return STST_OK;
+}
+
+STST_EXPORT int stst_slab_get_info(stst_slab *slab, stst_slab_info *info) {
+    if (!slab || !info)
+        return report(STST_ERR_INVALID_ARGUMENT, "null argument");
+    return guarded([&] {
+        slab->impl->info(*info);
+        return STST_OK;
+    });
+}
+
+STST_EXPORT int stst_slab_get_ipc_handle(stst_slab *slab, unsigned char handle[64]) {
+    if (!slab || !handle)
+        return report(STST_ERR_INVALID_ARGUMENT, "null argument");
+    return guarded([&] {
+        sc::internal::check(stst_ipc_get_mem_handle(slab->impl->device_base(), handle),
+                            "stst_ipc_get_mem_handle");
+        return STST_OK;
+    });
+}
+
+STST_EXPORT int stst_slab_attach_ipc(stst_slab *slab, int side, const unsigned char handle[64],
+                                     size_t peer_row_lo, size_t peer_row_hi) {
+    if (!slab || !handle || side < 0 || side > 1)
+        return report(STST_ERR_INVALID_ARGUMENT, "bad argument");
+    return guarded([&] {
+        sc::internal::check(stst_set_device(slab->impl->device()), "stst_set_device");
+        void *mapped = nullptr;
+        sc::internal::check(stst_ipc_open_mem_handle(handle, &mapped), "stst_ipc_open_mem_handle");
+        slab->impl->ipc_mappings.push_back(mapped);
+        slab->impl->attach(side, mapped, peer_row_lo, peer_row_hi);
+        return STST_OK;
+    });
+}
+
+STST_EXPORT int stst_slab_attach_local(stst_slab *slab, int side, stst_slab *peer) {
+    if (!slab || !peer || side < 0 || side > 1)
+        return report(STST_ERR_INVALID_ARGUMENT, "bad argument");
+    return guarded([&] {
+        stst_slab_info theirs;
+        peer->impl->info(theirs);
+        if (peer->impl->device() != slab->impl->device()) {
+            int can = 0;
+            sc::internal::check(stst_peer_can_access(slab->impl->device(), peer->impl->device(), &can),
+                                "stst_peer_can_access");
+            if (!can)
+                throw std::runtime_error("the two slabs' devices cannot access each other");
+            sc::internal::check(stst_peer_enable(slab->impl->device(), peer->impl->device()),
+                                "stst_peer_enable");
+        }
+        slab->impl->attach(side, peer->impl->device_base(), theirs.row_lo, theirs.row_hi);
+        return STST_OK;
+    });
+}
+
+STST_EXPORT int stst_slab_copy_from_host(stst_slab *slab, const void *cells, size_t bytes) {
+    if (!slab || !cells)
+        return report(STST_ERR_INVALID_ARGUMENT, "null argument");
+    return guarded([&] {
+        stst_slab_info info;
+        slab->impl->info(info);
+        if (bytes != (info.row_hi - info.row_lo) * info.grid_cols * slab->impl->cell_bytes())
+            return report(STST_ERR_RANGE, "The target buffer has not the same size as the slab");
+        slab->impl->upload(cells);
+        return STST_OK;
+    });
+}
+
+STST_EXPORT int stst_slab_copy_to_host(stst_slab *slab, void *cells, size_t bytes) {
+    if (!slab || !cells)
+        return report(STST_ERR_INVALID_ARGUMENT, "null argument");
+    return guarded([&] {
+        stst_slab_info info;
+        slab->impl->info(info);
+        if (bytes != (info.row_hi - info.row_lo) * info.grid_cols * slab->impl->cell_bytes())
+            return report(STST_ERR_RANGE, "The target buffer has not the same size as the slab");
+        slab->impl->download(cells);
+        return STST_OK;
+    });
+}
+
+STST_EXPORT int stst_slab_exchange_halos(stst_slab *slab) {
+    if (!slab)
+        return report(STST_ERR_INVALID_ARGUMENT, "null argument");
+    return guarded([&] {
+        slab->impl->exchange();
+        return STST_OK;
+    });
+}
+
+STST_EXPORT int stst_slab_update(stst_slab *slab, const stst_update_params *params) {
+    if (!slab || !params)
+        return report(STST_ERR_INVALID_ARGUMENT, "null argument");
+    return guarded([&] {
+        slab->impl->update(*params);
+        return STST_OK;
+    });
+}
+
+STST_EXPORT int stst_slab_synchronize(stst_slab *slab) {
+    if (!slab)
+        return report(STST_ERR_INVALID_ARGUMENT, "null argument");
+    return guarded([&] {
+        slab->impl->synchronize();
+        return STST_OK;
+    });
+}
+
+STST_EXPORT int stst_slab_record_event(stst_slab *slab, void *event) {
+    if (!slab || !event)
+        return report(STST_ERR_INVALID_ARGUMENT, "null argument");
+    return guarded([&] {
+        slab->impl->record(event);
+        return STST_OK;
+    });
 }

@@ -30,6 +30,7 @@
 #include "../Stencil.hpp"
 #include "Grid.hpp"
 #include "internal/Helpers.hpp"
+#include "internal/Launch.hpp"
 #include "internal/Planner.hpp"
 #include "internal/Runtime.hpp"
 #include "internal/TileKernel.hpp"
@@ -96,7 +97,7 @@ template <concepts::TransitionFunction F, bool split_cell_structure = false> cla
 
     StencilUpdate(Params params)
         : params(params), n_processed_cells(0), walltime(0.0), n_launches(0), last_plan(),
-          profile_events() {}
+          tensor_maps(), profile_events() {}
 
     /**
      * Compute `n_iterations` iterations of the source grid and return the result as a new grid.
@@ -149,10 +150,6 @@ template <concepts::TransitionFunction F, bool split_cell_structure = false> cla
     internal::LaunchPlan const &get_last_plan() const { return last_plan; }
 
   private:
-    static constexpr int CW = internal::column_group_width<Cell>();
-    // Rotating the register window by unrolling only pays for light-weight cells.
-    static constexpr bool kRotate = sizeof(Cell) <= 8;
-
     GridImpl run_simulation(GridImpl &source_grid) {
         if (params.n_iterations == 0) {
             return source_grid;
@@ -217,57 +214,16 @@ template <concepts::TransitionFunction F, bool split_cell_structure = false> cla
 
     void launch(internal::LaunchPlan const &plan, internal::GridStorage<Cell> &src,
                 internal::GridStorage<Cell> &dst, std::size_t iteration0, unsigned n_gens) {
-#if defined(__CUDACC__)
         using namespace internal;
-        constexpr unsigned n_sub = unsigned(F::n_subiterations);
-        constexpr unsigned radius = unsigned(F::stencil_radius);
-
-        SweepGeometry geo{};
-        geo.grid_h = unsigned(src.height);
-        geo.grid_w = unsigned(src.width);
-        geo.buf_row0 = 0;
-        geo.out_row_lo = 0;
-        geo.out_row_hi = int(src.height);
-        geo.tile_h = plan.tile_h;
-        geo.tile_w = plan.tile_w;
-        geo.halo = n_gens * n_sub * radius;
-        geo.hpad = plan.hpad;
-        geo.n_gens = n_gens;
-        geo.tiles_x = (geo.grid_w + geo.tile_w - 1) / geo.tile_w;
-        geo.use_tma = plan.use_tma ? 1u : 0u;
-        geo.iteration0 = iteration0;
-        const unsigned tiles_y = (geo.grid_h + geo.tile_h - 1) / geo.tile_h;
-
-        // Time-dependent values: evaluated on the host, exactly once per iteration.
-        TdvArray<TDV> tdvs{};
-        for (unsigned g = 0; g < n_gens; g++)
-            tdvs.v[g] = params.transition_function.get_time_dependent_value(iteration0 + g);
-
-        const unsigned rows = geo.tile_h + 2 * geo.halo;
-        const unsigned cols = plan.block_x * unsigned(CW);
-        const std::size_t smem =
-            tile_buffer_bytes<Cell>(rows, cols) * ((n_gens * n_sub > 1) ? 2 : 1);
-
-        TensorMapSet maps{};
-        if (plan.use_tma) {
-            for (std::size_t i = 0; i < Layout::n_planes; i++) {
-                STST_RT_CHECK(stst_tensor_map_encode_2d(
-                    &maps.map[i][0], src.planes.base[i], int(Layout::plane_bytes(i)), src.width,
-                    src.height, src.planes.pitch[i] * Layout::plane_bytes(i), cols, rows));
-            }
-        }
-
-        auto kernel = fused_sweep_kernel<F, CW, kRotate, 256, 1>;
-        static std::size_t configured_smem = 0;
-        if (smem > configured_smem) {
-            cudaError_t err = cudaFuncSetAttribute(
-                kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-            if (err != cudaSuccess)
-                throw std::runtime_error(std::string("StencilStream-B200: cannot reserve ") +
-                                         std::to_string(smem) + " bytes of shared memory: " +
-                                         cudaGetErrorString(err));
-            configured_smem = smem;
-        }
+        LaunchRegion region{};
+        region.device = src.device;
+        region.grid_h = unsigned(src.height);
+        region.grid_w = unsigned(src.width);
+        region.buf_row0 = 0;
+        region.buf_rows = src.height;
+        region.out_row_lo = 0;
+        region.out_row_hi = int(src.height);
+        region.tile_h = 0;
 
         std::shared_ptr<Event> start, stop;
         if (params.profiling) {
@@ -276,29 +232,15 @@ template <concepts::TransitionFunction F, bool split_cell_structure = false> cla
             start->record(src.stream);
         }
 
-        const dim3 block(plan.block_x, plan.block_y, 1);
-        const dim3 grid(geo.tiles_x * tiles_y, 1, 1);
-        kernel<<<grid, block, smem, static_cast<cudaStream_t>(src.stream)>>>(
-            params.transition_function, params.halo_value, tdvs, src.planes, dst.planes, maps, geo);
-        cudaError_t err = cudaGetLastError();
-        if (err != cudaSuccess)
-            throw std::runtime_error(std::string("StencilStream-B200: kernel launch failed: ") +
-                                     cudaGetErrorString(err));
+        SweepLauncher<F>::launch(plan, params.transition_function, params.halo_value, src.planes,
+                                 dst.planes, nullptr, region, iteration0, n_gens, tensor_maps,
+                                 src.stream);
         n_launches++;
 
         if (params.profiling) {
             stop->record(src.stream);
             profile_events.emplace_back(std::move(start), std::move(stop));
         }
-#else
-        (void)plan;
-        (void)src;
-        (void)dst;
-        (void)iteration0;
-        (void)n_gens;
-        throw std::runtime_error("StencilStream-B200 must be compiled with nvcc for sm_100a; "
-                                 "there is no CPU fallback");
-#endif
     }
 
     Params params;
@@ -306,6 +248,7 @@ template <concepts::TransitionFunction F, bool split_cell_structure = false> cla
     double walltime;
     std::size_t n_launches;
     internal::LaunchPlan last_plan;
+    internal::TensorMapCache<Cell> tensor_maps;
     std::vector<std::pair<std::shared_ptr<internal::Event>, std::shared_ptr<internal::Event>>>
         profile_events;
 };

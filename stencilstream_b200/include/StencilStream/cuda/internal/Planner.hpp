@@ -10,7 +10,7 @@
  * `halo = radius * n_subiterations * fused iterations` is the one used here.
  *
  * Every choice can be overridden, in this order of precedence: `StencilUpdate::Params` fields
- * (fused_iterations, tile_rows), then the environment (STST_FUSE, STST_TILE_ROWS, STST_BLOCK_Y,
+ * (fused_iterations — an upper bound, clamped to what fits into shared memory — and tile_rows), then the environment (STST_FUSE, STST_TILE_ROWS, STST_BLOCK_Y,
  * STST_BLOCK_X, STST_TMA), then the built-in heuristic.
  */
 #pragma once
@@ -199,31 +199,43 @@ LaunchPlan make_plan(int device, unsigned grid_h, unsigned grid_w, std::size_t n
     unsigned best_k = 0;
     TileShape best{};
     if (fused_override > 0) {
-        best_k = std::min(fused_override, k_cap);
-        best = evaluate(best_k, ctas_per_sm);
-        if (!best.feasible)
-            best = evaluate(best_k, 1);
-        if (!best.feasible)
-            throw std::invalid_argument("StencilStream-B200: fused_iterations=" +
-                                        std::to_string(best_k) +
-                                        " does not fit into shared memory for this cell type");
+        // `fused_iterations` is an upper bound: take the deepest fusion not exceeding it whose tile
+        // still fits into shared memory.
+        for (unsigned k = std::min(fused_override, k_cap); k >= 1 && best_k == 0; k--) {
+            TileShape s = evaluate(k, ctas_per_sm);
+            if (!s.feasible)
+                s = evaluate(k, 1);
+            if (s.feasible) {
+                best_k = k;
+                best = s;
+            }
+        }
+        if (best_k == 0)
+            throw std::invalid_argument(
+                "StencilStream-B200: cell type too large for a shared-memory tile");
     } else {
         // Cost model in "HBM-byte equivalents" per cell-iteration.
         const double hbm_bytes = 2.0 * double(sizeof(Cell)) * n_sub; // one read + one write / sweep
         const double onchip = 0.55 * double(sizeof(Cell)) * n_sub + 1.0 * n_sub;
         double best_cost = 0.0;
-        for (unsigned k = 1; k <= k_cap; k++) {
-            TileShape s = evaluate(k, ctas_per_sm);
-            if (!s.feasible)
-                s = evaluate(k, 1);
-            if (!s.feasible || s.efficiency < 0.35)
-                continue;
-            const double cost = std::max(hbm_bytes / k, onchip) / s.efficiency;
-            if (best_k == 0 || cost < best_cost * 0.97) {
-                best_k = k;
-                best = s;
-                best_cost = cost;
+        // Tiles that waste most of their footprint on halo are not considered, unless (tiny grids)
+        // nothing else exists.
+        for (double min_efficiency : {0.35, 0.0}) {
+            for (unsigned k = 1; k <= k_cap; k++) {
+                TileShape s = evaluate(k, ctas_per_sm);
+                if (!s.feasible)
+                    s = evaluate(k, 1);
+                if (!s.feasible || s.efficiency < min_efficiency)
+                    continue;
+                const double cost = std::max(hbm_bytes / k, onchip) / s.efficiency;
+                if (best_k == 0 || cost < best_cost * 0.97) {
+                    best_k = k;
+                    best = s;
+                    best_cost = cost;
+                }
             }
+            if (best_k != 0)
+                break;
         }
         if (best_k == 0)
             throw std::invalid_argument(

@@ -1,0 +1,451 @@
+/*
+ * StencilStream-B200 — the multi-GPU partitioner: one row slab of a grid per GPU, depth-k halos
+ * pushed to the neighbours over NVLink while the interior is being computed.
+ *
+ * The reference's cuda backend is single-device (StencilStream/cuda/StencilUpdate.hpp:83, :124-127),
+ * so this component has no counterpart there; what it must preserve is the observable result of the
+ * reference's generation loop (:212-273) on the whole grid. The temporal-blocking rules it relies on
+ * are the reference's own for its tiled FPGA pipeline: a pass that fuses k iterations consumes a halo
+ * of k * n_subiterations * radius cells (StencilStream/tiling/internal/StencilUpdateKernel.hpp:79-99).
+ *
+ * Decomposition. GPU g owns the global rows [row_lo, row_hi) of every plane and keeps `ghost` further
+ * rows on each side, ghost = k * n_sub * r for the fusion depth k fixed at construction. A slab holds
+ * two complete plane sets (ping/pong) and two 32-bit flags in ONE cudaMalloc block, so that a single
+ * IPC handle (or, within a process, a peer mapping) makes all of it addressable by the neighbours.
+ *
+ * One pass (= one fused launch over the slab, advancing it by n_gens <= k iterations), epoch e:
+ *
+ *   boundary stream:  wait  flag_from_up >= e+1, flag_from_down >= e+1      (ghosts of epoch e in place)
+ *                     wait  interior launch of epoch e-1
+ *                     sweep the top and bottom `ghost` rows of the slab; the kernel stores them into
+ *                           the own target planes AND into the neighbours' ghost rows (HaloPush)
+ *                     signal neighbours: their flag_from_{down,up} = e+2
+ *   interior stream:  wait  boundary launches of epoch e-1
+ *                     sweep the remaining rows (they depend on no ghost row)
+ *
+ * so the exchange for the next pass overlaps the interior sweep of this one, and nothing but the
+ * two small boundary launches ever waits for a neighbour. Flags are waited for with
+ * cuStreamWaitValue32 (stream-ordered, no host involvement, works across processes) and raised by a
+ * one-thread kernel behind the boundary sweep (system-scope fence + store). The flag protocol also
+ * covers the write-after-read hazards of the ping/pong buffers: a neighbour can only write ghost rows
+ * of buffer B in its epoch e+1 after it saw flag e+2, which is raised after this slab's epoch-e
+ * boundary launches — the last readers of those ghost rows — have finished.
+ *
+ * Who provides the neighbours' addresses is not decided here: `attach()` takes raw pointers. Within a
+ * process they come from another SlabUpdate (peer access enabled), across processes from
+ * cudaIpcOpenMemHandle (see the stst_slab_* C ABI in include/stst_workloads.h, and
+ * stencilstream_b200/sharding.py, which moves the handles with torch.distributed).
+ */
+#pragma once
+#include "Helpers.hpp"
+#include "Launch.hpp"
+#include "Planner.hpp"
+#include "Runtime.hpp"
+#include "TileKernel.hpp"
+
+#include <algorithm>
+#include <climits>
+#include <cstdint>
+#include <cstdlib>
+#include <memory>
+#include <stdexcept>
+#include <vector>
+
+namespace stencil {
+namespace cuda {
+namespace internal {
+
+#if defined(__CUDACC__)
+/// Raise a flag in (possibly remote) device memory once everything before it in the stream is done.
+__global__ void raise_flag_kernel(volatile unsigned *flag, unsigned value) {
+    __threadfence_system();
+    *flag = value;
+    __threadfence_system();
+}
+#endif
+
+/// Byte layout of a slab's single device allocation; a pure function of its shape, so that a
+/// neighbour can address into a mapped slab knowing only that slab's row range.
+template <typename Cell> struct SlabLayout {
+    using Layout = CellLayout<Cell>;
+    static constexpr std::size_t flag_bytes = 256; ///< [0]: flag_from_up, [1]: flag_from_down
+
+    std::size_t width, owned_rows, ghost, buf_rows;
+    std::size_t pitch[max_planes];        ///< elements between rows, per plane
+    std::size_t plane_offset[2][max_planes]; ///< byte offset of plane i of buffer b
+    std::size_t total_bytes;
+
+    SlabLayout(std::size_t width, std::size_t owned_rows, std::size_t ghost)
+        : width(width), owned_rows(owned_rows), ghost(ghost), buf_rows(owned_rows + 2 * ghost),
+          pitch{}, plane_offset{}, total_bytes(0) {
+        std::size_t offset = flag_bytes;
+        for (int b = 0; b < 2; b++) {
+            for (std::size_t i = 0; i < Layout::n_planes; i++) {
+                const std::size_t elem = Layout::plane_bytes(i);
+                std::size_t p = std::max<std::size_t>(width, 1);
+                while ((p * elem) % 128 != 0)
+                    p++;
+                pitch[i] = p;
+                plane_offset[b][i] = offset;
+                const std::size_t bytes = p * buf_rows * elem;
+                offset += (bytes + 255) / 256 * 256;
+            }
+        }
+        total_bytes = offset;
+    }
+
+    PlaneSet planes(void *base, int buffer) const {
+        PlaneSet set{};
+        for (std::size_t i = 0; i < Layout::n_planes; i++) {
+            set.base[i] = static_cast<unsigned char *>(base) + plane_offset[buffer][i];
+            set.pitch[i] = pitch[i];
+        }
+        return set;
+    }
+
+    static unsigned *flag(void *base, int which) { return static_cast<unsigned *>(base) + which; }
+};
+
+/// Rows [lo, hi) owned by shard `index` of `count` when `rows` rows are dealt out as evenly as
+/// possible (the first `rows % count` shards get one row more).
+inline void partition_rows(std::size_t rows, std::size_t count, std::size_t index, std::size_t &lo,
+                           std::size_t &hi) {
+    const std::size_t base = rows / count, extra = rows % count;
+    lo = index * base + std::min(index, extra);
+    hi = lo + base + (index < extra ? 1 : 0);
+}
+
+enum class SlabSide : int { up = 0, down = 1 };
+
+template <typename F> class SlabUpdate {
+  public:
+    using Cell = typename F::Cell;
+    using Layout = CellLayout<Cell>;
+
+    struct Config {
+        std::size_t grid_rows, grid_cols; ///< extent of the WHOLE grid
+        std::size_t row_lo, row_hi;       ///< global rows owned by this slab
+        int device;
+        unsigned fused_iterations; ///< upper bound for k; 0 = planner's choice. Must resolve to the
+                                   ///< same k on every slab of a grid (checked by the caller).
+        unsigned tile_rows;
+        bool overlap; ///< boundary-first scheduling (else one launch per pass)
+    };
+
+    explicit SlabUpdate(Config const &config)
+        : cfg(config), plan(make_plan<F>(config.device, unsigned(config.row_hi - config.row_lo),
+                                         unsigned(config.grid_cols), max_fused_iterations,
+                                         config.fused_iterations, config.tile_rows)),
+          ghost(std::size_t(plan.fused_iterations) * F::n_subiterations * F::stencil_radius),
+          layout(config.grid_cols, config.row_hi - config.row_lo, ghost), base(nullptr), epoch(0),
+          n_launches(0), interior_stream(nullptr), boundary_stream(nullptr) {
+        if (cfg.row_hi <= cfg.row_lo || cfg.row_hi > cfg.grid_rows)
+            throw std::invalid_argument("StencilStream-B200: illegal slab row range");
+        if (cfg.grid_rows > 0x7fffffffull || cfg.grid_cols > 0x7fffffffull)
+            throw std::range_error("StencilStream-B200 grids are limited to 2^31-1 rows/columns");
+        const bool has_neighbour = cfg.row_lo > 0 || cfg.row_hi < cfg.grid_rows;
+        if (has_neighbour && owned_rows() < ghost)
+            throw std::invalid_argument(
+                "StencilStream-B200: a slab must own at least k*n_sub*radius rows (its neighbour's "
+                "ghost rows must come from one slab); use fewer GPUs or a smaller fused_iterations");
+        STST_RT_CHECK(stst_malloc_ipc(cfg.device, layout.total_bytes, &base));
+        STST_RT_CHECK(stst_stream_create(cfg.device, 0, &interior_stream));
+        STST_RT_CHECK(stst_stream_create(cfg.device, 1, &boundary_stream));
+        STST_RT_CHECK(stst_memset_async(base, 0, SlabLayout<Cell>::flag_bytes, interior_stream));
+        STST_RT_CHECK(stst_stream_synchronize(interior_stream));
+        for (int s = 0; s < 2; s++) {
+            peer_base[s] = nullptr;
+            peer_row_lo[s] = peer_row_hi[s] = 0;
+        }
+    }
+
+    SlabUpdate(SlabUpdate const &) = delete;
+    SlabUpdate &operator=(SlabUpdate const &) = delete;
+
+    ~SlabUpdate() {
+        (void)stst_stream_synchronize(interior_stream);
+        (void)stst_stream_synchronize(boundary_stream);
+        (void)stst_stream_destroy(interior_stream);
+        (void)stst_stream_destroy(boundary_stream);
+        (void)stst_free_ipc(cfg.device, base);
+    }
+
+    // ---- topology ---------------------------------------------------------------------------------
+
+    /// The slab's device allocation (export it with stst_ipc_get_mem_handle, or hand it to a slab
+    /// of the same process).
+    void *device_base() const { return base; }
+    std::size_t device_bytes() const { return layout.total_bytes; }
+    std::size_t owned_rows() const { return cfg.row_hi - cfg.row_lo; }
+    std::size_t ghost_rows() const { return ghost; }
+    bool has_up() const { return cfg.row_lo > 0; }
+    bool has_down() const { return cfg.row_hi < cfg.grid_rows; }
+    LaunchPlan const &get_plan() const { return plan; }
+    Config const &get_config() const { return cfg; }
+    std::size_t get_n_launches() const { return n_launches; }
+    std::size_t get_epoch() const { return epoch; }
+    stst_stream_t stream() const { return interior_stream; }
+
+    /// Make the neighbouring slab on `side`, mapped at `mapped_base` in this process and owning the
+    /// global rows [row_lo, row_hi), the target of this slab's halo pushes.
+    void attach(SlabSide side, void *mapped_base, std::size_t row_lo, std::size_t row_hi) {
+        const int s = int(side);
+        if (side == SlabSide::up ? row_hi != cfg.row_lo : row_lo != cfg.row_hi)
+            throw std::invalid_argument("StencilStream-B200: attached slab is not adjacent");
+        if (row_hi - row_lo < ghost)
+            throw std::invalid_argument("StencilStream-B200: attached slab owns too few rows");
+        peer_base[s] = mapped_base;
+        peer_row_lo[s] = row_lo;
+        peer_row_hi[s] = row_hi;
+    }
+
+    // ---- data ---------------------------------------------------------------------------------------
+
+    /// Replace the owned rows by `cells` (dense row-major array of whole cells, owned_rows x width).
+    /// Asynchronous on stream(); `cells` should be pinned and must stay valid until synchronize().
+    void upload(const Cell *cells) {
+        transfer</*to_device=*/true>(const_cast<Cell *>(cells));
+    }
+
+    /// Copy the owned rows of the current generation into `cells`. Returns after the copy is done.
+    void download(Cell *cells) {
+        join_streams();
+        transfer</*to_device=*/false>(cells);
+        STST_RT_CHECK(stst_stream_synchronize(interior_stream));
+    }
+
+    /// Publish the owned boundary rows of the current buffer to the neighbours' ghost rows (needed
+    /// once after upload(); afterwards every pass pushes its own boundary rows). Collective: every
+    /// slab of the grid has to call it at the same point of its sequence of operations.
+    void exchange_halos() {
+        join_streams();
+        // A fresh pair of epochs (same buffer parity): flag values raised for earlier passes must
+        // not satisfy the waits of the passes that follow this exchange.
+        epoch += 2;
+        const int cur = int(epoch & 1);
+        const PlaneSet mine = layout.planes(base, cur);
+        for (int s = 0; s < 2; s++) {
+            if (!has_side(s))
+                continue;
+            require_attached(s);
+            const SlabLayout<Cell> peer(cfg.grid_cols, peer_row_hi[s] - peer_row_lo[s], ghost);
+            const PlaneSet theirs = peer.planes(peer_base[s], cur);
+            // rows I own next to that neighbour, and where they live in its planes
+            const std::size_t my_first = (s == 0) ? ghost : ghost + owned_rows() - ghost;
+            const std::size_t their_first = (s == 0) ? ghost + peer.owned_rows : 0;
+            for (std::size_t i = 0; i < Layout::n_planes; i++) {
+                const std::size_t row_bytes = layout.pitch[i] * Layout::plane_bytes(i);
+                STST_RT_CHECK(stst_memcpy_d2d_async(
+                    static_cast<unsigned char *>(theirs.base[i]) + their_first * row_bytes,
+                    static_cast<const unsigned char *>(mine.base[i]) + my_first * row_bytes,
+                    ghost * row_bytes, boundary_stream));
+            }
+            raise_flag(s, unsigned(epoch + 1));
+        }
+        fork_streams();
+    }
+
+    // ---- the generation loop --------------------------------------------------------------------------
+
+    /// Enqueue `n_iterations` iterations starting at global iteration `iteration_offset`.
+    void run(F const &tf, Cell const &halo_value, std::size_t iteration_offset,
+             std::size_t n_iterations) {
+        const std::size_t k = plan.fused_iterations;
+        std::size_t iteration = iteration_offset;
+        std::size_t remaining = n_iterations;
+        while (remaining > 0) {
+            const unsigned n_gens = unsigned(std::min(remaining, k));
+            pass(tf, halo_value, iteration, n_gens);
+            iteration += n_gens;
+            remaining -= n_gens;
+        }
+    }
+
+    /// Record `event` behind everything enqueued on this slab so far (both streams).
+    void record(stst_event_t event) {
+        join_streams();
+        STST_RT_CHECK(stst_event_record(event, interior_stream));
+    }
+
+    /// Wait until everything enqueued on this slab has finished.
+    void synchronize() {
+        STST_RT_CHECK(stst_stream_synchronize(boundary_stream));
+        STST_RT_CHECK(stst_stream_synchronize(interior_stream));
+    }
+
+  private:
+    bool has_side(int s) const { return s == 0 ? has_up() : has_down(); }
+
+    void require_attached(int s) const {
+        if (!peer_base[s])
+            throw std::logic_error("StencilStream-B200: neighbouring slab not attached");
+    }
+
+    unsigned *my_flag(int s) const { return SlabLayout<Cell>::flag(base, s); }
+
+    /// The flag INSIDE neighbour s that this slab raises: the up neighbour sees me as "down".
+    unsigned *peer_flag(int s) const { return SlabLayout<Cell>::flag(peer_base[s], 1 - s); }
+
+    void raise_flag(int s, unsigned value) {
+#if defined(__CUDACC__)
+        select_device();
+        raise_flag_kernel<<<1, 1, 0, static_cast<cudaStream_t>(boundary_stream)>>>(peer_flag(s), value);
+        if (cudaGetLastError() != cudaSuccess)
+            throw std::runtime_error("StencilStream-B200: flag kernel launch failed");
+        n_launches++;
+#else
+        (void)s, (void)value;
+        throw std::runtime_error("StencilStream-B200 must be compiled with nvcc for sm_100a");
+#endif
+    }
+
+    void select_device() {
+#if defined(__CUDACC__)
+        int current = -1;
+        if (cudaGetDevice(&current) != cudaSuccess || current != cfg.device)
+            cudaSetDevice(cfg.device);
+#endif
+    }
+
+    /// boundary stream waits for the interior stream and vice versa
+    void join_streams() {
+        // Re-recording an event does not disturb waits that were enqueued on its earlier state.
+        boundary_done.record(boundary_stream);
+        STST_RT_CHECK(stst_stream_wait_event(interior_stream, boundary_done.get()));
+        interior_done.record(interior_stream);
+        STST_RT_CHECK(stst_stream_wait_event(boundary_stream, interior_done.get()));
+    }
+
+    void fork_streams() { join_streams(); }
+
+    void pass(F const &tf, Cell const &halo_value, std::size_t iteration0, unsigned n_gens) {
+        const int cur = int(epoch & 1);
+        const PlaneSet src = layout.planes(base, cur);
+        const PlaneSet dst = layout.planes(base, cur ^ 1);
+
+        HaloPush push{};
+        push.up_row_hi = INT_MIN;
+        push.down_row_lo = INT_MAX;
+        for (int s = 0; s < 2; s++) {
+            if (!has_side(s))
+                continue;
+            require_attached(s);
+            const SlabLayout<Cell> peer(cfg.grid_cols, peer_row_hi[s] - peer_row_lo[s], ghost);
+            const PlaneSet theirs = peer.planes(peer_base[s], cur ^ 1);
+            if (s == 0) {
+                push.up = theirs;
+                push.up_buf_row0 = int(peer_row_lo[s]) - int(ghost);
+                push.up_row_hi = int(cfg.row_lo + ghost);
+            } else {
+                push.down = theirs;
+                push.down_buf_row0 = int(peer_row_lo[s]) - int(ghost);
+                push.down_row_lo = int(cfg.row_hi - ghost);
+            }
+        }
+        const bool pushes = has_up() || has_down();
+
+        LaunchRegion region{};
+        region.device = cfg.device;
+        region.grid_h = unsigned(cfg.grid_rows);
+        region.grid_w = unsigned(cfg.grid_cols);
+        region.buf_row0 = int(cfg.row_lo) - int(ghost);
+        region.buf_rows = layout.buf_rows;
+
+        // Everything launched in this pass reads rows written by BOTH streams in the previous pass.
+        join_streams();
+        for (int s = 0; s < 2; s++) {
+            if (has_side(s))
+                STST_RT_CHECK(stst_stream_wait_value32_geq(boundary_stream, my_flag(s),
+                                                           unsigned(epoch + 1)));
+        }
+
+        auto sweep = [&](std::size_t lo, std::size_t hi, bool with_push, bool strip,
+                         stst_stream_t stream) {
+            if (hi <= lo)
+                return;
+            region.out_row_lo = int(lo);
+            region.out_row_hi = int(hi);
+            region.tile_h = strip ? unsigned(hi - lo) : 0;
+            SweepLauncher<F>::launch(plan, tf, halo_value, src, dst,
+                                     (with_push && pushes) ? &push : nullptr, region, iteration0,
+                                     n_gens, tensor_maps, stream);
+            n_launches++;
+        };
+
+        const bool split = cfg.overlap && pushes && owned_rows() > 2 * ghost;
+        if (split) {
+            const std::size_t top_hi = has_up() ? cfg.row_lo + ghost : cfg.row_lo;
+            const std::size_t bottom_lo = has_down() ? cfg.row_hi - ghost : cfg.row_hi;
+            sweep(cfg.row_lo, top_hi, true, true, boundary_stream);
+            sweep(bottom_lo, cfg.row_hi, true, true, boundary_stream);
+            for (int s = 0; s < 2; s++)
+                if (has_side(s))
+                    raise_flag(s, unsigned(epoch + 2));
+            sweep(top_hi, bottom_lo, false, false, interior_stream);
+        } else {
+            sweep(cfg.row_lo, cfg.row_hi, true, false, boundary_stream);
+            for (int s = 0; s < 2; s++)
+                if (has_side(s))
+                    raise_flag(s, unsigned(epoch + 2));
+        }
+        epoch++;
+    }
+
+    template <bool to_device> void transfer(Cell *cells) {
+#if defined(__CUDACC__)
+        select_device();
+        const int cur = int(epoch & 1);
+        PlaneSet planes = layout.planes(base, cur);
+        const std::size_t width = cfg.grid_cols;
+        const std::size_t row_bytes = std::max<std::size_t>(width * sizeof(Cell), 1);
+        const std::size_t chunk_rows =
+            std::max<std::size_t>(1, std::min<std::size_t>(owned_rows(), (std::size_t(64) << 20) / row_bytes));
+        void *staging[2] = {device_alloc(cfg.device, chunk_rows * width * sizeof(Cell), interior_stream),
+                            device_alloc(cfg.device, chunk_rows * width * sizeof(Cell), interior_stream)};
+        std::size_t chunk = 0;
+        for (std::size_t row = 0; row < owned_rows(); row += chunk_rows, chunk++) {
+            const std::size_t rows = std::min(chunk_rows, owned_rows() - row);
+            const std::size_t n = rows * width;
+            Cell *stage = static_cast<Cell *>(staging[chunk & 1]);
+            const unsigned block = 256;
+            const unsigned grid =
+                unsigned(std::min<std::size_t>((n + block - 1) / block, std::size_t(148) * 16));
+            auto s = static_cast<cudaStream_t>(interior_stream);
+            if constexpr (to_device) {
+                STST_RT_CHECK(stst_memcpy_h2d_async(stage, cells + row * width, n * sizeof(Cell),
+                                                    interior_stream));
+                scatter_cells_kernel<Cell><<<grid, block, 0, s>>>(stage, planes, width, ghost + row, n);
+            } else {
+                gather_cells_kernel<Cell><<<grid, block, 0, s>>>(stage, planes, width, ghost + row, n);
+                STST_RT_CHECK(stst_memcpy_d2h_async(cells + row * width, stage, n * sizeof(Cell),
+                                                    interior_stream));
+            }
+            if (cudaGetLastError() != cudaSuccess)
+                throw std::runtime_error("StencilStream-B200: layout kernel launch failed");
+        }
+        device_free(cfg.device, staging[0], interior_stream);
+        device_free(cfg.device, staging[1], interior_stream);
+#else
+        (void)cells;
+        throw std::runtime_error("StencilStream-B200 must be compiled with nvcc for sm_100a; "
+                                 "there is no CPU fallback");
+#endif
+    }
+
+    Config cfg;
+    LaunchPlan plan;
+    std::size_t ghost;
+    SlabLayout<Cell> layout;
+    void *base;
+    std::size_t epoch;
+    std::size_t n_launches;
+    stst_stream_t interior_stream, boundary_stream;
+    void *peer_base[2];
+    std::size_t peer_row_lo[2], peer_row_hi[2];
+    TensorMapCache<Cell> tensor_maps;
+    Event boundary_done, interior_done;
+};
+
+} // namespace internal
+} // namespace cuda
+} // namespace stencil

@@ -58,6 +58,7 @@ struct SweepGeometry {
     unsigned n_gens;         ///< iterations fused into this launch (>= 1)
     unsigned tiles_x;        ///< tiles per tile-row (blockIdx.x = ty * tiles_x + tx)
     unsigned use_tma;        ///< non-zero: stage tiles with TMA box loads (maps valid)
+    unsigned push;           ///< non-zero: also store result rows into neighbour slabs (HaloPush valid)
     unsigned long long iteration0; ///< global index of the first fused iteration
 };
 
@@ -68,6 +69,21 @@ template <typename TDV> struct TdvArray {
 /// One 128-byte TMA descriptor per plane (only read when SweepGeometry::use_tma != 0).
 struct alignas(64) TensorMapSet {
     unsigned char map[max_planes][128];
+};
+
+/**
+ * Halo push of a row-sharded run (see SlabUpdate.hpp): while a launch writes its result rows, the
+ * rows the neighbouring slabs need as ghosts for THEIR next launch are additionally stored straight
+ * into the neighbours' planes — peer memory, reached over NVLink through a peer- or IPC-mapped
+ * address — so that the transfer rides along with the sweep instead of following it as a copy.
+ * Global rows below `up_row_hi` go to the upper neighbour, rows from `down_row_lo` on to the lower
+ * one; `*_buf_row0` is the global row held in plane row 0 of that neighbour's planes.
+ */
+struct HaloPush {
+    PlaneSet up, down;
+    int up_buf_row0, down_buf_row0;
+    int up_row_hi;   ///< INT_MIN if there is nothing to push upwards
+    int down_row_lo; ///< INT_MAX if there is nothing to push downwards
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -337,8 +353,8 @@ __device__ __forceinline__ void
 sweep_rows(F const &tf, typename F::Cell const &halo_value,
            typename F::TimeDependentValue const &tdv, std::size_t iteration,
            TileView<typename F::Cell> const &in, TileView<typename F::Cell> const &out,
-           bool to_global, PlaneSet const &dst, SweepGeometry const &geo, int gy0, int gx0,
-           int row_lo, int row_hi) {
+           bool to_global, PlaneSet const &dst, HaloPush const &push, SweepGeometry const &geo,
+           int gy0, int gx0, int row_lo, int row_hi) {
     using Cell = typename F::Cell;
     using TDV = typename F::TimeDependentValue;
     using L = CellLayout<Cell>;
@@ -437,24 +453,33 @@ sweep_rows(F const &tf, typename F::Cell const &halo_value,
                 if (gy < geo.out_row_lo || gy >= geo.out_row_hi || gy >= int(geo.grid_h))
                     return;
             }
-            for_each_plane<Cell>([&](auto I) {
-                using T = typename L::template plane_t<I>;
-                T *g = static_cast<T *>(dst.base[I]) +
-                       (long long)(gy - geo.buf_row0) * (long long)dst.pitch[I] + gxg;
-                if (kInterior || gxg + CW <= int(geo.grid_w)) {
-                    Pack<T, CW> q;
+            auto store_row = [&](PlaneSet const &planes, int buf_row0) {
+                for_each_plane<Cell>([&](auto I) {
+                    using T = typename L::template plane_t<I>;
+                    T *g = static_cast<T *>(planes.base[I]) +
+                           (long long)(gy - buf_row0) * (long long)planes.pitch[I] + gxg;
+                    if (kInterior || gxg + CW <= int(geo.grid_w)) {
+                        Pack<T, CW> q;
 #pragma unroll
-                    for (int i = 0; i < CW; i++)
-                        q.v[i] = L::template get<I>(result[i]);
-                    *reinterpret_cast<Pack<T, CW> *>(g) = q;
-                } else {
+                        for (int i = 0; i < CW; i++)
+                            q.v[i] = L::template get<I>(result[i]);
+                        *reinterpret_cast<Pack<T, CW> *>(g) = q;
+                    } else {
 #pragma unroll
-                    for (int i = 0; i < CW; i++) {
-                        if (gxg + i < int(geo.grid_w))
-                            g[i] = L::template get<I>(result[i]);
+                        for (int i = 0; i < CW; i++) {
+                            if (gxg + i < int(geo.grid_w))
+                                g[i] = L::template get<I>(result[i]);
+                        }
                     }
-                }
-            });
+                });
+            };
+            store_row(dst, geo.buf_row0);
+            if (geo.push) {
+                if (gy < push.up_row_hi)
+                    store_row(push.up, push.up_buf_row0);
+                if (gy >= push.down_row_lo)
+                    store_row(push.down, push.down_buf_row0);
+            }
         }
     };
 
@@ -498,8 +523,9 @@ template <typename F, int CW, bool kInterior, bool kRotate>
 __device__ __forceinline__ void
 run_tile(F const &tf, typename F::Cell const &halo_value,
          TdvArray<typename F::TimeDependentValue> const &tdvs, PlaneSet const &src,
-         PlaneSet const &dst, TensorMapSet const &maps, SweepGeometry const &geo,
-         unsigned char *smem, unsigned long long *mbar, int gy0, int gx0) {
+         PlaneSet const &dst, HaloPush const &push, TensorMapSet const &maps,
+         SweepGeometry const &geo, unsigned char *smem, unsigned long long *mbar, int gy0,
+         int gx0) {
     using Cell = typename F::Cell;
     constexpr int R = int(F::stencil_radius);
     constexpr unsigned n_sub = unsigned(F::n_subiterations);
@@ -526,8 +552,8 @@ run_tile(F const &tf, typename F::Cell const &halo_value,
                     TileView<Cell> const &in = (step & 1u) ? buf1 : buf0;
                     TileView<Cell> const &out = (step & 1u) ? buf0 : buf1;
                     sweep_rows<F, CW, kInterior, kRotate, Subs>(tf, halo_value, tdv, iteration, in,
-                                                                out, last, dst, geo, gy0, gx0, lo,
-                                                                hi);
+                                                                out, last, dst, push, geo, gy0,
+                                                                gx0, lo, hi);
                     if (!last)
                         __syncthreads();
                     step++;
@@ -548,6 +574,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
                        const __grid_constant__ typename F::Cell halo_value,
                        const __grid_constant__ TdvArray<typename F::TimeDependentValue> tdvs,
                        const __grid_constant__ PlaneSet src, const __grid_constant__ PlaneSet dst,
+                       const __grid_constant__ HaloPush push,
                        const __grid_constant__ TensorMapSet maps,
                        const __grid_constant__ SweepGeometry geo) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -573,11 +600,11 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
                           tile_gx + int(geo.tile_w + geo.hpad) <= int(geo.grid_w);
 
     if (interior) {
-        run_tile<F, CW, true, kRotate>(tf, halo_value, tdvs, src, dst, maps, geo, smem, &mbar, gy0,
-                                       gx0);
+        run_tile<F, CW, true, kRotate>(tf, halo_value, tdvs, src, dst, push, maps, geo, smem, &mbar,
+                                       gy0, gx0);
     } else {
-        run_tile<F, CW, false, false>(tf, halo_value, tdvs, src, dst, maps, geo, smem, &mbar, gy0,
-                                      gx0);
+        run_tile<F, CW, false, false>(tf, halo_value, tdvs, src, dst, push, maps, geo, smem, &mbar,
+                                      gy0, gx0);
     }
 }
 

@@ -1,0 +1,240 @@
+"""Row-sharded generation loop: one process per GPU, one slab of the grid per process.
+
+Host-side mirror of the multi-GPU partitioner in
+stencilstream_b200/include/StencilStream/cuda/internal/SlabUpdate.hpp (C ABI: the `stst_slab_*`
+functions of include/stst_workloads.h). The reference's cuda backend is single-device
+(reference StencilStream/cuda/StencilUpdate.hpp:83), so there is no reference interface to mirror for
+the sharding itself; the object below keeps the shape of the reference's `StencilUpdate`
+(`Params`, call operator advancing by `n_iterations`, `get_params()` live reference) and adds what a
+slab needs: `load()` for the owned rows and `to_numpy()` to read them back.
+
+`torch.distributed` is plumbing only: it moves the 64-byte CUDA IPC handle and the row range of every
+slab to its two neighbours once, at construction. The data path has no collective — every fused
+launch stores the boundary rows straight into the neighbours' ghost rows over NVLink and the slabs
+order themselves with stream-ordered device flags.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Any, Callable
+
+import numpy as np
+
+from . import _native
+from .api import Params, StencilStreamError, _as_param_struct, _check
+
+
+def partition_rows(rows: int, count: int, index: int) -> tuple[int, int]:
+    """Rows [lo, hi) owned by shard `index` of `count`: as even as possible, the first
+    `rows % count` shards one row larger (same rule as internal::partition_rows in SlabUpdate.hpp)."""
+    if count <= 0 or not 0 <= index < count:
+        raise ValueError("illegal shard index")
+    base, extra = divmod(rows, count)
+    lo = index * base + min(index, extra)
+    return lo, lo + base + (1 if index < extra else 0)
+
+
+class SlabInfo(C.Structure):
+    _fields_ = [
+        ("grid_rows", C.c_size_t), ("grid_cols", C.c_size_t), ("row_lo", C.c_size_t),
+        ("row_hi", C.c_size_t), ("ghost_rows", C.c_size_t), ("device_bytes", C.c_size_t),
+        ("n_launches", C.c_size_t), ("epoch", C.c_size_t), ("device", C.c_int),
+        ("fused_iterations", C.c_uint), ("tile_h", C.c_uint), ("tile_w", C.c_uint),
+        ("block_x", C.c_uint), ("block_y", C.c_uint), ("use_tma", C.c_uint), ("overlap", C.c_uint),
+        ("smem_bytes", C.c_size_t),
+    ]
+
+
+def _slab_lib(strict: bool | None = None):
+    lib = _native.workloads_lib(strict)
+    if not getattr(lib, "_slab_prototypes", False):
+        vp = C.c_void_p
+        lib.stst_slab_create.argtypes = [C.c_char_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_size_t,
+                                         C.c_int, C.c_uint, C.c_uint, C.c_int, C.POINTER(vp)]
+        lib.stst_slab_destroy.argtypes = [vp]
+        lib.stst_slab_get_info.argtypes = [vp, C.POINTER(SlabInfo)]
+        lib.stst_slab_get_ipc_handle.argtypes = [vp, C.c_char_p]
+        lib.stst_slab_attach_ipc.argtypes = [vp, C.c_int, C.c_char_p, C.c_size_t, C.c_size_t]
+        lib.stst_slab_attach_local.argtypes = [vp, C.c_int, vp]
+        lib.stst_slab_copy_from_host.argtypes = [vp, vp, C.c_size_t]
+        lib.stst_slab_copy_to_host.argtypes = [vp, vp, C.c_size_t]
+        lib.stst_slab_exchange_halos.argtypes = [vp]
+        lib.stst_slab_update.argtypes = [vp, C.POINTER(_native.UpdateParams)]
+        lib.stst_slab_synchronize.argtypes = [vp]
+        lib.stst_slab_record_event.argtypes = [vp, vp]
+        lib._slab_prototypes = True
+    return lib
+
+
+class NativeSlab:
+    """ctypes handle to one `stst_slab` (sm_100a kernels; fails loudly without a CUDA device)."""
+
+    def __init__(self, workload: str, grid_rows: int, grid_cols: int, row_lo: int, row_hi: int,
+                 device: int, fused_iterations: int = 0, tile_rows: int = 0, overlap: bool = True,
+                 strict: bool | None = None):
+        self.workload = workload
+        self.dtype = _native.CELL_DTYPES[workload]
+        self._lib = _slab_lib(strict)
+        handle = C.c_void_p()
+        _check(self._lib, self._lib.stst_slab_create(
+            workload.encode(), grid_rows, grid_cols, row_lo, row_hi, device, fused_iterations,
+            tile_rows, int(bool(overlap)), C.byref(handle)))
+        self._handle = handle
+        self._keepalive = None
+
+    def close(self) -> None:
+        handle = getattr(self, "_handle", None)
+        if handle:
+            self._lib.stst_slab_destroy(handle)
+            self._handle = None
+
+    __del__ = close
+
+    def info(self) -> SlabInfo:
+        info = SlabInfo()
+        _check(self._lib, self._lib.stst_slab_get_info(self._handle, C.byref(info)))
+        return info
+
+    def ipc_handle(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        _check(self._lib, self._lib.stst_slab_get_ipc_handle(self._handle, buf))
+        return buf.raw
+
+    def attach_ipc(self, side: int, handle: bytes, row_lo: int, row_hi: int) -> None:
+        _check(self._lib, self._lib.stst_slab_attach_ipc(self._handle, side, handle, row_lo, row_hi))
+
+    def attach_local(self, side: int, peer: "NativeSlab") -> None:
+        _check(self._lib, self._lib.stst_slab_attach_local(self._handle, side, peer._handle))
+
+    def copy_from_host(self, cells: np.ndarray) -> None:
+        arr = np.ascontiguousarray(cells, dtype=self.dtype)
+        self._keepalive = arr  # the copy may still be in flight when this returns
+        _check(self._lib, self._lib.stst_slab_copy_from_host(
+            self._handle, arr.ctypes.data_as(C.c_void_p), arr.nbytes))
+
+    def copy_to_host(self, out: np.ndarray) -> None:
+        if out.dtype != self.dtype or not out.flags["C_CONTIGUOUS"]:
+            raise ValueError("copy_to_host needs a C-contiguous array of the workload's cell dtype")
+        _check(self._lib, self._lib.stst_slab_copy_to_host(
+            self._handle, out.ctypes.data_as(C.c_void_p), out.nbytes))
+
+    def exchange_halos(self) -> None:
+        _check(self._lib, self._lib.stst_slab_exchange_halos(self._handle))
+
+    def update(self, native_params) -> None:
+        _check(self._lib, self._lib.stst_slab_update(self._handle, C.byref(native_params)))
+
+    def synchronize(self) -> None:
+        _check(self._lib, self._lib.stst_slab_synchronize(self._handle))
+
+    def record_event(self, event) -> None:
+        _check(self._lib, self._lib.stst_slab_record_event(self._handle, event))
+
+
+class ShardedStencilUpdate:
+    """The generation loop on this process's slab of a `grid_rows x grid_cols` grid.
+
+    Every process of the group constructs one with the same arguments except `rank`/`device`
+    (construction is collective: it exchanges slab handles), then issues the same sequence of
+    `load()` and calls. `comm` is `torch.distributed` (or anything with `all_gather_object`);
+    `slab_factory` builds the slab object (the product default is `NativeSlab`; the CPU test-suite
+    injects a host-memory double to exercise this module without a GPU).
+    """
+
+    def __init__(self, workload: str, params: Params, grid_rows: int, grid_cols: int, *, rank: int,
+                 world: int, device: int = 0, comm: Any = None, overlap: bool = True,
+                 strict: bool | None = None,
+                 slab_factory: Callable[..., Any] | None = None):
+        if world > 1 and comm is None:
+            raise ValueError("a process group is needed to exchange slab handles")
+        self.workload, self.params = workload, params
+        self.grid_rows, self.grid_cols = int(grid_rows), int(grid_cols)
+        self.rank, self.world, self.device = rank, world, device
+        self.row_lo, self.row_hi = partition_rows(self.grid_rows, world, rank)
+        self.dtype = _native.CELL_DTYPES[workload]
+        factory = slab_factory or (lambda **kw: NativeSlab(strict=strict, **kw))
+
+        def make(fused):
+            return factory(workload=workload, grid_rows=self.grid_rows, grid_cols=self.grid_cols,
+                           row_lo=self.row_lo, row_hi=self.row_hi, device=device,
+                           fused_iterations=fused, tile_rows=int(params.tile_rows), overlap=overlap)
+
+        self.slab = make(int(params.fused_iterations))
+        if world > 1:
+            # All slabs must fuse the same number of iterations (it fixes the ghost depth).
+            depths = [None] * world
+            comm.all_gather_object(depths, int(self.slab.info().fused_iterations))
+            if len(set(depths)) != 1:
+                self.slab.close()
+                self.slab = make(min(depths))
+            mine = (self.slab.ipc_handle(), self.row_lo, self.row_hi,
+                    int(self.slab.info().fused_iterations))
+            everyone = [None] * world
+            comm.all_gather_object(everyone, mine)
+            if len({e[3] for e in everyone}) != 1:
+                raise StencilStreamError("slabs disagree on the fusion depth")
+            for side, other in ((0, rank - 1), (1, rank + 1)):
+                if 0 <= other < world:
+                    handle, lo, hi, _ = everyone[other]
+                    self.slab.attach_ipc(side, handle, lo, hi)
+        self._keepalive = None
+
+    # -- data ---------------------------------------------------------------------------------------
+    @property
+    def owned_shape(self) -> tuple[int, int]:
+        return (self.row_hi - self.row_lo, self.grid_cols)
+
+    def load(self, cells: np.ndarray) -> None:
+        """Replace the owned rows by `cells` (shape `owned_shape`) and publish the boundary rows to
+        the neighbours' ghost rows. Collective."""
+        if tuple(cells.shape) != self.owned_shape:
+            from .api import RangeError
+            raise RangeError("The target buffer has not the same size as the slab")
+        self.slab.copy_from_host(cells)
+        self.slab.exchange_halos()
+
+    def to_numpy(self, out: np.ndarray | None = None) -> np.ndarray:
+        if out is None:
+            out = np.empty(self.owned_shape, dtype=self.dtype)
+        self.slab.copy_to_host(out)
+        return out
+
+    # -- the reference's StencilUpdate surface ----------------------------------------------------------
+    def get_params(self) -> Params:
+        return self.params
+
+    def _native_params(self):
+        p = self.params
+        tf = _as_param_struct(self.workload, p.transition_function)
+        native = _native.UpdateParams()
+        native.transition_function = C.addressof(tf)
+        native.transition_function_bytes = C.sizeof(tf)
+        halo = None
+        if p.halo_value is not None:
+            halo = np.zeros((), dtype=self.dtype)
+            halo[()] = p.halo_value
+            native.halo_value = halo.ctypes.data
+            native.halo_value_bytes = halo.nbytes
+        native.iteration_offset = int(p.iteration_offset)
+        native.n_iterations = int(p.n_iterations)
+        native.blocking = int(bool(p.blocking))
+        self._keepalive = (tf, halo)
+        return native
+
+    def __call__(self) -> "ShardedStencilUpdate":
+        """Advance the slab by `params.n_iterations` iterations starting at `params.iteration_offset`
+        (asynchronous unless `params.blocking`). Collective."""
+        self.slab.update(self._native_params())
+        return self
+
+    def synchronize(self) -> None:
+        self.slab.synchronize()
+
+    def get_n_launches(self) -> int:
+        return int(self.slab.info().n_launches)
+
+    def info(self) -> SlabInfo:
+        return self.slab.info()
+
+    def close(self) -> None:
+        self.slab.close()

@@ -120,3 +120,31 @@ def rel_max_norm(a, b):
         else:
             worst = max(worst, float(np.abs(a64 - b64).max() / scale))
     return worst
+
+
+# ---- golden vectors (tests/golden/*.npz, generated from the reference-built oracle) ----------------
+
+GOLDEN_DIR = __import__("pathlib").Path(__file__).resolve().parent / "golden"
+GOLDEN_WORKLOADS = ["conway", "jacobi5", "jacobi9", "jacobi_r2", "jacobi_r3", "hotspot", "fdtd",
+                    "convection_pt", "convection_thermal", "kat", "kat_r2"]
+
+
+def load_golden(workload):
+    """Returns dict(params=ctypes struct, halo=cell or None, input, output, iteration_offset,
+    n_iterations) of the fixture tests/golden/<workload>.npz."""
+    import ctypes as C
+    data = np.load(GOLDEN_DIR / f"{workload}.npz")
+    dtype = _native.CELL_DTYPES[workload]
+    shape = tuple(int(x) for x in data["shape"])
+    cells_in = np.ascontiguousarray(data["input"]).view(dtype).reshape(shape)
+    cells_out = np.ascontiguousarray(data["output"]).view(dtype).reshape(shape)
+    params = _native.PARAM_TYPES[workload]()
+    raw = data["params"].tobytes()
+    assert len(raw) == C.sizeof(params)
+    C.memmove(C.addressof(params), raw, len(raw))
+    halo = None
+    if bool(data["has_halo"]):
+        halo = np.frombuffer(data["halo"].tobytes(), dtype=dtype)[0]
+    return {"params": params, "halo": halo, "input": cells_in, "output": cells_out,
+            "iteration_offset": int(data["iteration_offset"]),
+            "n_iterations": int(data["n_iterations"])}

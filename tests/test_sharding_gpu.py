@@ -1,0 +1,27 @@
+"""The multi-GPU partitioner on real hardware: `world` processes, one slab each, neighbours mapped
+through CUDA IPC, halos pushed by the fused sweep kernel, ordering by stream-ordered flags.
+
+The processes use device `rank % device_count`, so the whole protocol (IPC mapping, peer stores, flag
+waits) is also exercised on a one-GPU box, where all slabs live on the same device. The gathered
+result must equal the CPU oracle's update of the whole grid bit for bit (-fmad=false build).
+"""
+import pytest
+
+from test_sharding_cpu import run_group
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("mode", ["cuda", "cuda-no-overlap"])
+@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("workload,shape,offset,n,depth", [
+    ("hotspot", (330, 700), 0, 7, 3),
+    ("kat", (97, 260), 5, 5, 2),
+    ("fdtd", (150, 333), 3, 4, 2),
+    ("jacobi_r3", (200, 520), 0, 5, 2),
+    ("conway", (333, 640), 0, 9, 4),
+    ("convection_pt", (120, 96), 0, 3, 1),
+    ("jacobi5", (1000, 1030), 0, 20, 4),
+])
+def test_sharded_update_equals_whole_grid_on_gpu(mode, world, workload, shape, offset, n, depth, built):
+    run_group(world, workload, shape, offset, n, depth, mode)
