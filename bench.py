@@ -298,12 +298,17 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             import torch
             torch.cuda.synchronize()
 
+    host_memory = {"kind": "pinned"}
+
     def pinned_cells(n_rows):
-        """A numpy view of pinned host memory for n_rows x cols cells."""
+        """A numpy view of pinned host memory for n_rows x cols cells (pageable if the box refuses
+        to pin that much)."""
         ptr = C.c_void_p()
         n_bytes = n_rows * cols * dtype.itemsize
         if timer.rt.stst_malloc_host(n_bytes, C.byref(ptr)) != 0:
-            raise RuntimeError(timer.rt.stst_last_error().decode())
+            host_memory["kind"] = "pageable (cudaHostAlloc failed: " + \
+                timer.rt.stst_last_error().decode()[-40:] + ")"
+            return np.empty((n_rows, cols), dtype=dtype)
         raw = (C.c_ubyte * n_bytes).from_address(ptr.value)
         return np.frombuffer(raw, dtype=dtype, count=n_rows * cols).reshape(n_rows, cols)
 
@@ -410,7 +415,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     else:
         # Per rank: owned rows from pinned host memory -> slab (H2D + layout + halo exchange), the
         # update, owned rows back into pinned host memory. Wall clock between barriers, max over ranks.
-        host_out = pinned_cells(rows)
+        host_out = host_in  # results overwrite the inputs: one host buffer per rank
         runner.get_params().blocking = True
         e2e_steps = max(1, min(args.steps, 3))
         times = []
@@ -431,7 +436,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         e2e = {"value": total_cells * iters / float(np.mean(times)) / 1e9, "unit": "GCell-updates/s",
                "h2d_bytes_per_step": int(rows * cols * dtype.itemsize) * world,
                "d2h_bytes_per_step": int(rows * cols * dtype.itemsize) * world,
-               "ms_per_step": float(np.mean(times) * 1e3), "checksum": checksum}
+               "ms_per_step": float(np.mean(times) * 1e3), "checksum": checksum,
+               "host_memory": host_memory["kind"]}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

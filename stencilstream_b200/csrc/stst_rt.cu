@@ -34,6 +34,7 @@ int fail(int code, const char *what, const char *detail) {
     do {                                                                                           \
         cudaError_t err__ = (call);                                                                \
         if (err__ != cudaSuccess) {                                                                \
+            (void)cudaGetLastError(); /* do not leave it for an unrelated later check */           \
             return fail(int(err__), #call, cudaGetErrorString(err__));                             \
         }                                                                                          \
     } while (0)

@@ -23,6 +23,7 @@
 #include <sycl/sycl.hpp>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <stdexcept>
@@ -49,8 +50,8 @@ template <typename Cell> class GridStorage {
 
     GridStorage(std::size_t height, std::size_t width, int device)
         : height(height), width(width), device(device), stream(default_stream(device)),
-          planes{}, device_block(nullptr), host(nullptr), host_current(true),
-          device_current(true) {
+          planes{}, device_block(nullptr), host(nullptr), host_is_pinned(false),
+          host_current(true), device_current(true) {
         if (height > 0x7fffffffull || width > 0x7fffffffull)
             throw std::range_error("StencilStream-B200 grids are limited to 2^31-1 rows/columns");
     }
@@ -63,7 +64,10 @@ template <typename Cell> class GridStorage {
         if (host) {
             // The mirror may still be the source/target of an in-flight copy.
             (void)stst_stream_synchronize(stream);
-            pinned_free(host);
+            if (host_is_pinned)
+                pinned_free(host);
+            else
+                std::free(host);
         }
     }
 
@@ -97,8 +101,21 @@ template <typename Cell> class GridStorage {
     }
 
     void allocate_host() {
-        if (!host)
-            host = static_cast<Cell *>(pinned_alloc(std::max<std::size_t>(n_cells(), 1) * sizeof(Cell)));
+        if (host)
+            return;
+        const std::size_t bytes = std::max<std::size_t>(n_cells(), 1) * sizeof(Cell);
+        void *p = nullptr;
+        if (stst_malloc_host(bytes, &p) == 0) {
+            host_is_pinned = true;
+        } else {
+            // The machine refuses to pin that much memory: an ordinary (pageable) mirror still
+            // works, transfers are just staged by the driver and slower.
+            p = std::aligned_alloc(4096, (bytes + 4095) / 4096 * 4096);
+            if (!p)
+                throw std::bad_alloc();
+            host_is_pinned = false;
+        }
+        host = static_cast<Cell *>(p);
     }
 
     std::size_t n_cells() const { return height * width; }
@@ -227,6 +244,7 @@ template <typename Cell> class GridStorage {
 
     void *device_block;
     Cell *host;
+    bool host_is_pinned;
     bool host_current, device_current;
 
   public:

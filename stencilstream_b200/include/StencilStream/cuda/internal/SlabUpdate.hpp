@@ -148,6 +148,10 @@ template <typename F> class SlabUpdate {
             throw std::invalid_argument(
                 "StencilStream-B200: a slab must own at least k*n_sub*radius rows (its neighbour's "
                 "ghost rows must come from one slab); use fewer GPUs or a smaller fused_iterations");
+        // Events, streams and launches below belong to cfg.device: make it current for this thread.
+        STST_RT_CHECK(stst_set_device(cfg.device));
+        boundary_done = std::make_unique<Event>();
+        interior_done = std::make_unique<Event>();
         STST_RT_CHECK(stst_malloc_ipc(cfg.device, layout.total_bytes, &base));
         STST_RT_CHECK(stst_stream_create(cfg.device, 0, &interior_stream));
         STST_RT_CHECK(stst_stream_create(cfg.device, 1, &boundary_stream));
@@ -310,10 +314,11 @@ template <typename F> class SlabUpdate {
     /// boundary stream waits for the interior stream and vice versa
     void join_streams() {
         // Re-recording an event does not disturb waits that were enqueued on its earlier state.
-        boundary_done.record(boundary_stream);
-        STST_RT_CHECK(stst_stream_wait_event(interior_stream, boundary_done.get()));
-        interior_done.record(interior_stream);
-        STST_RT_CHECK(stst_stream_wait_event(boundary_stream, interior_done.get()));
+        select_device();
+        boundary_done->record(boundary_stream);
+        STST_RT_CHECK(stst_stream_wait_event(interior_stream, boundary_done->get()));
+        interior_done->record(interior_stream);
+        STST_RT_CHECK(stst_stream_wait_event(boundary_stream, interior_done->get()));
     }
 
     void fork_streams() { join_streams(); }
@@ -443,7 +448,7 @@ template <typename F> class SlabUpdate {
     void *peer_base[2];
     std::size_t peer_row_lo[2], peer_row_hi[2];
     TensorMapCache<Cell> tensor_maps;
-    Event boundary_done, interior_done;
+    std::unique_ptr<Event> boundary_done, interior_done;
 };
 
 } // namespace internal
