@@ -13,6 +13,6 @@ for W in $WL; do
   timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --workload $W --gpus $N --steps 3 --warmup 3 > gpurun_out/scale_${W}_$N.json 2> gpurun_out/scale_${W}_$N.err
   tail -3 gpurun_out/scale_${W}_$N.err | cut -c1-300
   cat gpurun_out/scale_${W}_$N.json
-  timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --workload $W --gpus $N --steps 3 --warmup 3 --no-overlap > gpurun_out/scale_${W}_${N}_noverlap.json 2> gpurun_out/scale_${W}_${N}_noverlap.err
+  [ "$4" = "noverlap" ] && timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --workload $W --gpus $N --steps 3 --warmup 3 --no-overlap > gpurun_out/scale_${W}_${N}_noverlap.json 2> gpurun_out/scale_${W}_${N}_noverlap.err
   cut -c1-200 gpurun_out/scale_${W}_${N}_noverlap.json
 done
