@@ -1,0 +1,62 @@
+"""Build-time source annotator: make a StencilStream user's functors callable from nvcc device code.
+
+nvcc has no "device by default" mode, and the reference's example functors carry no
+`__host__ __device__`. The one mechanical rule this tool applies to a copy of
+the user's sources in the build tree:
+
+    every function whose first parameter is a `Stencil<...> const &` gets the prefix `STST_HD`
+    (= `__host__ __device__` under nvcc, nothing under a host compiler),
+
+which covers the transition function's `operator()` and helpers that receive the stencil (e.g. the
+FDTD material resolvers' `get_material_coefficients`). Nothing else is touched; constructors and
+`get_time_dependent_value` stay host-only (the latter is evaluated on the host, reference
+StencilStream/cuda/StencilUpdate.hpp:224). The sources under version control remain unmodified —
+include path and CMake target stay the only hand-made differences.
+
+    python -m stencilstream_b200.tools.annotate SRC [SRC ...] -o OUT_DIR
+"""
+from __future__ import annotations
+
+import argparse
+import re
+from pathlib import Path
+
+# `<indent><return type and qualifiers> name(Stencil<` — the declarator starts a line in the
+# reference's clang-format style; the return type may not contain ';', '{', '}' or '('.
+_DECL = re.compile(
+    r"^(?P<indent>[ \t]*)(?P<head>(?!return\b|else\b|STST_HD\b)[A-Za-z_:][^;{}()\n]*?[\s&*>])"
+    r"(?P<name>operator\s*\(\s*\)|[A-Za-z_]\w*)\s*\(\s*(?:const\s+)?(?:stencil::)?Stencil\s*<",
+    re.M)
+
+
+def annotate_text(text: str) -> tuple[str, int]:
+    """Returns the annotated text and the number of functions that were prefixed."""
+    count = 0
+
+    def repl(m: re.Match) -> str:
+        nonlocal count
+        count += 1
+        return f"{m.group('indent')}STST_HD {m.group('head')}{m.group('name')}{m.group(0)[m.end('name') - m.start(0):]}"
+
+    return _DECL.sub(repl, text), count
+
+
+def annotate_file(src: Path, dst: Path) -> int:
+    text, count = annotate_text(src.read_text())
+    dst.parent.mkdir(parents=True, exist_ok=True)
+    dst.write_text(text)
+    return count
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser(description=__doc__.split("\n")[0])
+    ap.add_argument("sources", nargs="+", type=Path)
+    ap.add_argument("-o", "--out-dir", type=Path, required=True)
+    args = ap.parse_args()
+    for src in args.sources:
+        n = annotate_file(src, args.out_dir / src.name)
+        print(f"{src} -> {args.out_dir / src.name}: {n} function(s) annotated")
+
+
+if __name__ == "__main__":
+    main()
