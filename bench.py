@@ -44,7 +44,14 @@ if str(ROOT) not in sys.path:
 WORKLOAD_LABEL = {
     "jacobi5": "Jacobi 5-point fp32 {rows}x{cols}, {iters} generations (BASELINE.json configs[1])",
     "hotspot": "Rodinia HotSpot fp32 temp+power {rows}x{cols}, {iters} generations (BASELINE.json configs[2])",
+    "fdtd": "FDTD micro-cavity max_grid experiment {rows}x{cols} (coef cells, E/H sub-iterations, tdv source "
+            "wave), {iters} time steps (BASELINE.json configs[3])",
+    "convection_pt": "Mantle convection pseudo-transient kernel fp64 {rows}x{cols}, {iters} iterations "
+                     "(BASELINE.json configs[4])",
 }
+# (rows per GPU, cols, iterations per step, scaling) used when the command line does not say otherwise
+DEFAULTS = {"jacobi5": (16384, 16384, 1000, "weak"), "hotspot": (16384, 16384, 1000, "weak"),
+            "fdtd": (4608, 4608, 1000, "strong"), "convection_pt": (4096, 8192, 100, "weak")}
 DTYPE = {"jacobi5": "f32", "hotspot": "f32", "fdtd": "f32", "convection_pt": "f64", "conway": "u8"}
 
 
@@ -61,6 +68,27 @@ def make_workload(name: str, rows: int, cols: int):
     if name == "hotspot":
         return W.hotspot_params(rows, cols), (0.0, 0.0), \
             lambda view, r0, r1, total: fill_hotspot(view, r0, r1, total, cols)
+    if name == "fdtd":
+        exp = W.FdtdExperiment(W.FDTD_MAX_GRID)
+        if (rows, cols) != (exp.grid_wh(), exp.grid_wh()):
+            raise SystemExit(f"bench.py: the max_grid experiment is {exp.grid_wh()} x {exp.grid_wh()}")
+        grid0 = {}
+
+        def fill_fdtd(view, r0, r1, total):
+            if "cells" not in grid0:
+                grid0["cells"] = exp.initial_grid()
+            view[...] = grid0["cells"][r0:r1]
+        return exp.kernel_params(), None, fill_fdtd
+    if name == "convection_pt":
+        exp = W.ConvectionExperiment(W.convection_benchmark_config(
+            res=cols, n_iters=1, lx=rows / cols, ly=1.0))
+        assert exp.grid_shape == (rows, cols), (exp.grid_shape, rows, cols)
+
+        def fill_convection(view, r0, r1, total):
+            for lo in range(r0, r1, 256):
+                hi = min(lo + 256, r1)
+                view[lo - r0:hi - r0] = exp.initial_grid(lo, hi)
+        return exp.pseudo_transient_params(), None, fill_convection
     raise SystemExit(f"bench.py: unsupported workload {name!r}")
 
 
@@ -232,7 +260,7 @@ def run_reference_arm(args, rank: int, world: int):
     line = {
         "impl": "reference", "metric": "GCell-updates/s", "value": value, "unit": "GCell-updates/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": DTYPE.get(args.workload, "f32"), "data": "synthetic",
         "config": {"workload": WORKLOAD_LABEL[args.workload].format(rows=rows, cols=cols, iters=iters),
                    "note": "reference StencilStream cpu backend on host cores; each step is a bounded "
@@ -273,10 +301,17 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         dist_mod.init_process_group("nccl", device_id=torch.device("cuda", device))
         dist = dist_mod
 
-    rows, cols, iters = args.rows, args.cols, args.iterations
     workload = args.workload
+    cols, iters, scaling = args.cols, args.iterations, args.scaling
+    if scaling == "weak":
+        rows, total_rows = args.rows, args.rows * world
+    else:  # strong: the grid is fixed, every rank owns a share of its rows
+        total_rows = args.rows
+        from stencilstream_b200.sharding import partition_rows
+        lo, hi = partition_rows(total_rows, world, rank)
+        rows = hi - lo
     info = workload_info(workload)
-    params, halo, fill = make_workload(workload, rows * world, cols)
+    params, halo, fill = make_workload(workload, total_rows, cols)
     dtype = _native.CELL_DTYPES[workload]
 
     runner = None
@@ -285,7 +320,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         runner = ShardedStencilUpdate(
             workload, Params(transition_function=params, halo_value=halo, n_iterations=iters,
                              blocking=False, fused_iterations=args.fuse),
-            rows * world, cols, rank=rank, world=world, device=device, comm=dist,
+            total_rows, cols, rank=rank, world=world, device=device, comm=dist,
             overlap=not args.no_overlap)
         timer = StreamTimer(device, record=runner.slab.record_event, sync=runner.synchronize)
     else:
@@ -330,7 +365,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             return update.get_n_launches()
     else:
         host_in = pinned_cells(rows)
-        fill(host_in, runner.row_lo, runner.row_hi, rows * world)
+        fill(host_in, runner.row_lo, runner.row_hi, total_rows)
         runner.load(host_in)
         runner.synchronize()
 
@@ -359,7 +394,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         elapsed_ms = float(t.item())
 
-    total_cells = rows * world * cols
+    total_cells = total_rows * cols
     ms_per_step = elapsed_ms / args.steps
     value = total_cells * iters / (ms_per_step * 1e-3) / 1e9
 
@@ -400,8 +435,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             timer.sync()
             t0 = time.perf_counter()
             result = e2e_update(host_grid)          # H2D upload + layout + all fused launches
-            checksum = float(result.accessor("read")[rows // 2, cols // 2]["temp"]
-                             if dtype.names else result.accessor("read")[rows // 2, cols // 2])  # D2H
+            mid = result.accessor("read")[rows // 2, cols // 2]  # D2H of the whole result grid
+            checksum = float(mid[dtype.names[0]] if dtype.names else mid)
             t1 = time.perf_counter()
             if i > 0:
                 times.append(t1 - t0)
@@ -432,7 +467,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             if i > 0:
                 times.append(float(t.item()))
         mid = host_out[rows // 2, cols // 2]
-        checksum = float(mid["temp"] if dtype.names else mid)
+        checksum = float(mid[dtype.names[0]] if dtype.names else mid)
         e2e = {"value": total_cells * iters / float(np.mean(times)) / 1e9, "unit": "GCell-updates/s",
                "h2d_bytes_per_step": int(rows * cols * dtype.itemsize) * world,
                "d2h_bytes_per_step": int(rows * cols * dtype.itemsize) * world,
@@ -447,10 +482,10 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         line = {
             "metric": "GCell-updates/s", "value": value, "unit": "GCell-updates/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
             "dtype": DTYPE.get(workload, "f32"), "data": "synthetic",
             "config": {
-                "workload": WORKLOAD_LABEL[workload].format(rows=rows * world, cols=cols, iters=iters),
+                "workload": WORKLOAD_LABEL[workload].format(rows=total_rows, cols=cols, iters=iters),
                 "rows_per_gpu": rows, "cols": cols, "iterations_per_step": iters,
                 "parallelism": f"row-sharded x{world}" if world > 1 else "single GPU",
                 "l2": "grid (>= 1 GiB per buffer) exceeds the 126 MB L2; no flush needed",
@@ -478,9 +513,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="jacobi5", choices=sorted(WORKLOAD_LABEL))
-    ap.add_argument("--rows", type=int, default=16384, help="rows per GPU")
-    ap.add_argument("--cols", type=int, default=16384)
-    ap.add_argument("--iterations", type=int, default=1000, help="iterations per step")
+    ap.add_argument("--rows", type=int, default=0,
+                    help="rows per GPU (weak scaling) or of the whole grid (strong scaling)")
+    ap.add_argument("--cols", type=int, default=0)
+    ap.add_argument("--iterations", type=int, default=0, help="iterations per step")
+    ap.add_argument("--scaling", default="", choices=["", "weak", "strong"])
     ap.add_argument("--fuse", type=int, default=0, help="fused iterations per launch (0 = planner)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-overlap", action="store_true",
@@ -492,6 +529,12 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.gpus != world and world > 1:
         args.gpus = world
+
+    d_rows, d_cols, d_iters, d_scaling = DEFAULTS[args.workload]
+    args.rows = args.rows or d_rows
+    args.cols = args.cols or d_cols
+    args.iterations = args.iterations or d_iters
+    args.scaling = args.scaling or d_scaling
 
     if args.impl == "reference":
         run_reference_arm(args, rank, world)
