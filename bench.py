@@ -315,7 +315,12 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     dtype = _native.CELL_DTYPES[workload]
 
     runner = None
-    if world > 1:
+    # Slabs whose host image would not fit comfortably into (pinned) host memory are generated and
+    # transferred in chunks of rows; that path uses the slab object on a single GPU as well.
+    slab_bytes = rows * cols * dtype.itemsize
+    chunked = slab_bytes > (args.chunk_above_gib << 30)
+    chunk_rows = max(1, min(rows, (256 << 20) // (cols * dtype.itemsize)))
+    if world > 1 or chunked:
         from stencilstream_b200.sharding import ShardedStencilUpdate
         runner = ShardedStencilUpdate(
             workload, Params(transition_function=params, halo_value=halo, n_iterations=iters,
@@ -363,12 +368,21 @@ def run_ours(args, rank: int, world: int, local_rank: int):
 
         def n_launches():
             return update.get_n_launches()
+    elif chunked:
+        host_in = pinned_cells(chunk_rows)
+
+        def generate(lo, hi):
+            fill(host_in[:hi - lo], lo, hi, total_rows)
+            return host_in[:hi - lo]
+        runner.load_chunks(generate, chunk_rows)
+        runner.synchronize()
     else:
         host_in = pinned_cells(rows)
         fill(host_in, runner.row_lo, runner.row_hi, total_rows)
         runner.load(host_in)
         runner.synchronize()
 
+    if runner is not None:
         def step():
             return runner()
 
@@ -457,16 +471,26 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         for i in range(1 + e2e_steps):
             barrier()
             t0 = time.perf_counter()
-            runner.load(host_in)
-            runner()
-            runner.to_numpy(host_out)
+            if chunked:  # the same pinned chunk buffer is the source and sink of every chunk
+                runner.load_chunks(lambda lo, hi: host_in[:hi - lo], chunk_rows)
+                runner()
+                for lo in range(0, rows, chunk_rows):
+                    n = min(chunk_rows, rows - lo)
+                    runner.slab.copy_rows_to_host(lo, host_in[:n])
+            else:
+                runner.load(host_in)
+                runner()
+                runner.to_numpy(host_out)
             t1 = time.perf_counter()
-            import torch
-            t = torch.tensor([t1 - t0], dtype=torch.float64, device=f"cuda:{device}")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            step_seconds = t1 - t0
+            if dist is not None:
+                import torch
+                t = torch.tensor([step_seconds], dtype=torch.float64, device=f"cuda:{device}")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                step_seconds = float(t.item())
             if i > 0:
-                times.append(float(t.item()))
-        mid = host_out[rows // 2, cols // 2]
+                times.append(step_seconds)
+        mid = host_out[min(rows // 2, host_out.shape[0] - 1), cols // 2]
         checksum = float(mid[dtype.names[0]] if dtype.names else mid)
         e2e = {"value": total_cells * iters / float(np.mean(times)) / 1e9, "unit": "GCell-updates/s",
                "h2d_bytes_per_step": int(rows * cols * dtype.itemsize) * world,
@@ -520,6 +544,8 @@ def main():
     ap.add_argument("--scaling", default="", choices=["", "weak", "strong"])
     ap.add_argument("--fuse", type=int, default=0, help="fused iterations per launch (0 = planner)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--chunk-above-gib", type=int, default=4,
+                    help="slabs larger than this many GiB are generated/transferred in row chunks")
     ap.add_argument("--no-overlap", action="store_true",
                     help="multi-GPU: one launch per pass instead of boundary-first scheduling")
     args = ap.parse_args()

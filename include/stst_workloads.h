@@ -248,6 +248,12 @@ int stst_slab_attach_local(stst_slab *slab, int side, stst_slab *peer);
  * copy_from_host is asynchronous when `cells` is pinned (stst_malloc_host / stst_host_register). */
 int stst_slab_copy_from_host(stst_slab *slab, const void *cells, size_t bytes);
 int stst_slab_copy_to_host(stst_slab *slab, void *cells, size_t bytes);
+/* The same for `n_rows` owned rows starting at slab-local row `first_row` (slabs larger than what
+ * the host wants to stage at once). */
+int stst_slab_copy_rows_from_host(stst_slab *slab, size_t first_row, size_t n_rows,
+                                  const void *cells, size_t bytes);
+int stst_slab_copy_rows_to_host(stst_slab *slab, size_t first_row, size_t n_rows, void *cells,
+                                size_t bytes);
 int stst_slab_exchange_halos(stst_slab *slab);
 /* Uses transition_function, halo_value, iteration_offset, n_iterations and blocking of `params`. */
 int stst_slab_update(stst_slab *slab, const stst_update_params *params);

@@ -163,13 +163,19 @@ def build_oracle_ref(force: bool = False, verbose: bool = False) -> Path | None:
 
 
 def build_all(force: bool = False, verbose: bool = False) -> dict:
-    out = {
-        "runtime": build_runtime(force=force, verbose=verbose),
-        "workloads": build_workloads(strict=False, force=force, verbose=verbose),
-        "workloads_strict": build_workloads(strict=True, force=force, verbose=verbose),
-        "oracle_port": build_oracle_port(force=force, verbose=verbose),
-        "oracle_ref": build_oracle_ref(force=force, verbose=verbose),
-    }
+    from concurrent.futures import ThreadPoolExecutor
+
+    out = {"runtime": build_runtime(force=force, verbose=verbose)}
+    # The two workloads libraries and the oracles are independent: compile them side by side.
+    with ThreadPoolExecutor(max_workers=4) as pool:
+        jobs = {
+            "workloads": pool.submit(build_workloads, False, force, verbose),
+            "workloads_strict": pool.submit(build_workloads, True, force, verbose),
+            "oracle_port": pool.submit(build_oracle_port, force, verbose),
+            "oracle_ref": pool.submit(build_oracle_ref, force, verbose),
+        }
+        for name, job in jobs.items():
+            out[name] = job.result()
     return out
 
 

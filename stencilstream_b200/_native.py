@@ -156,7 +156,8 @@ WORKLOADS_SYMBOLS = [
     "stst_update_set_params", "stst_update_apply", "stst_update_get_stats", "stst_update_destroy",
     "stst_slab_create", "stst_slab_destroy", "stst_slab_get_info", "stst_slab_get_ipc_handle",
     "stst_slab_attach_ipc", "stst_slab_attach_local", "stst_slab_copy_from_host",
-    "stst_slab_copy_to_host", "stst_slab_exchange_halos", "stst_slab_update", "stst_slab_synchronize",
+    "stst_slab_copy_to_host", "stst_slab_copy_rows_from_host", "stst_slab_copy_rows_to_host",
+    "stst_slab_exchange_halos", "stst_slab_update", "stst_slab_synchronize",
     "stst_slab_record_event",
 ]
 

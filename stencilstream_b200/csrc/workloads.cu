@@ -151,8 +151,8 @@ struct SlabBase {
     virtual void *device_base() = 0;
     virtual int device() const = 0;
     virtual void attach(int side, void *mapped, std::size_t lo, std::size_t hi) = 0;
-    virtual void upload(const void *cells) = 0;
-    virtual void download(void *cells) = 0;
+    virtual void upload(const void *cells, std::size_t first_row, std::size_t n_rows) = 0;
+    virtual void download(void *cells, std::size_t first_row, std::size_t n_rows) = 0;
     virtual void exchange() = 0;
     virtual void update(const stst_update_params &p) = 0;
     virtual void synchronize() = 0;
@@ -202,8 +202,12 @@ template <typename F, typename ParamBlock> struct SlabHolder final : SlabBase {
         slab->attach(side == 0 ? sc::internal::SlabSide::up : sc::internal::SlabSide::down, mapped,
                      lo, hi);
     }
-    void upload(const void *cells) override { slab->upload(static_cast<const Cell *>(cells)); }
-    void download(void *cells) override { slab->download(static_cast<Cell *>(cells)); }
+    void upload(const void *cells, std::size_t first_row, std::size_t n_rows) override {
+        slab->upload_rows(static_cast<const Cell *>(cells), first_row, n_rows);
+    }
+    void download(void *cells, std::size_t first_row, std::size_t n_rows) override {
+        slab->download_rows(static_cast<Cell *>(cells), first_row, n_rows);
+    }
     void exchange() override { slab->exchange_halos(); }
     void update(const stst_update_params &p) override {
         auto params = UpdateHolder<F, ParamBlock>::convert(p);
@@ -544,30 +548,47 @@ STST_EXPORT int stst_slab_attach_local(stst_slab *slab, int side, stst_slab *pee
     });
 }
 
-STST_EXPORT int stst_slab_copy_from_host(stst_slab *slab, const void *cells, size_t bytes) {
-    if (!slab || !cells)
+namespace {
+int slab_copy_rows(stst_slab *slab, void *cells, size_t bytes, size_t first_row, size_t n_rows,
+                   bool whole, bool to_device) {
+    if (!slab || (!cells && bytes != 0))
         return report(STST_ERR_INVALID_ARGUMENT, "null argument");
     return guarded([&] {
         stst_slab_info info;
         slab->impl->info(info);
-        if (bytes != (info.row_hi - info.row_lo) * info.grid_cols * slab->impl->cell_bytes())
-            return report(STST_ERR_RANGE, "The target buffer has not the same size as the slab");
-        slab->impl->upload(cells);
+        const size_t owned = info.row_hi - info.row_lo;
+        if (whole) {
+            first_row = 0;
+            n_rows = owned;
+        }
+        if (first_row > owned || n_rows > owned - first_row ||
+            bytes != n_rows * info.grid_cols * slab->impl->cell_bytes())
+            return report(STST_ERR_RANGE, "The target buffer has not the same size as the slab rows");
+        if (to_device)
+            slab->impl->upload(cells, first_row, n_rows);
+        else
+            slab->impl->download(cells, first_row, n_rows);
         return STST_OK;
     });
 }
+} // namespace
+
+STST_EXPORT int stst_slab_copy_from_host(stst_slab *slab, const void *cells, size_t bytes) {
+    return slab_copy_rows(slab, const_cast<void *>(cells), bytes, 0, 0, true, true);
+}
 
 STST_EXPORT int stst_slab_copy_to_host(stst_slab *slab, void *cells, size_t bytes) {
-    if (!slab || !cells)
-        return report(STST_ERR_INVALID_ARGUMENT, "null argument");
-    return guarded([&] {
-        stst_slab_info info;
-        slab->impl->info(info);
-        if (bytes != (info.row_hi - info.row_lo) * info.grid_cols * slab->impl->cell_bytes())
-            return report(STST_ERR_RANGE, "The target buffer has not the same size as the slab");
-        slab->impl->download(cells);
-        return STST_OK;
-    });
+    return slab_copy_rows(slab, cells, bytes, 0, 0, true, false);
+}
+
+STST_EXPORT int stst_slab_copy_rows_from_host(stst_slab *slab, size_t first_row, size_t n_rows,
+                                              const void *cells, size_t bytes) {
+    return slab_copy_rows(slab, const_cast<void *>(cells), bytes, first_row, n_rows, false, true);
+}
+
+STST_EXPORT int stst_slab_copy_rows_to_host(stst_slab *slab, size_t first_row, size_t n_rows,
+                                            void *cells, size_t bytes) {
+    return slab_copy_rows(slab, cells, bytes, first_row, n_rows, false, false);
 }
 
 STST_EXPORT int stst_slab_exchange_halos(stst_slab *slab) {

@@ -72,8 +72,15 @@ template <typename F> struct SweepLauncher {
     using TDV = typename F::TimeDependentValue;
     using Layout = CellLayout<Cell>;
     static constexpr int CW = column_group_width<Cell>();
-    // Rotating the register window by unrolling only pays for light-weight cells.
-    static constexpr bool kRotate = sizeof(Cell) <= 8;
+    // Register window: rotated by unrolling for light-weight cells, shifted for medium ones; fat
+    // cells re-read their neighbourhood from shared memory instead (see sweep_rows).
+#if defined(STST_WINDOW_MODE)
+    static constexpr int kMode = STST_WINDOW_MODE;
+#else
+    static constexpr int kMode = sizeof(Cell) <= 8    ? window_rotate
+                                 : sizeof(Cell) <= 16 ? window_shift
+                                                      : window_reload;
+#endif
 
     /**
      * Enqueue one fused launch on `stream`: iterations [iteration0, iteration0 + n_gens) of `tf`
@@ -135,7 +142,7 @@ template <typename F> struct SweepLauncher {
                                          std::to_string(region.device));
         }
 
-        auto kernel = fused_sweep_kernel<F, CW, kRotate, 256, 1>;
+        auto kernel = fused_sweep_kernel<F, CW, kMode, max_threads_per_cta<Cell>(), 1>;
         static std::size_t configured_smem_per_device[64] = {};
         std::size_t &configured_smem = configured_smem_per_device[region.device & 63];
         if (smem > configured_smem) {

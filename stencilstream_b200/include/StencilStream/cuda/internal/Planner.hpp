@@ -58,12 +58,26 @@ inline const stst_device_info &cached_device_info(int device) {
 
 /// Column-group width: 128-bit vectors of the widest plane element, at most 4 columns.
 template <typename Cell> constexpr int column_group_width() {
+    // Very fat cells (mantle convection: 11 doubles): one column per thread keeps the functor within
+    // 128 registers, which allows 512-thread CTAs (16 warps per SM instead of 8).
+    if (sizeof(Cell) > 64) {
+#if defined(STST_FAT_COLUMN_GROUP_WIDTH)
+        return STST_FAT_COLUMN_GROUP_WIDTH;
+#else
+        return 1;
+#endif
+    }
     const std::size_t widest = CellLayout<Cell>::max_plane_bytes();
     if (widest >= 16)
         return 1;
     if (widest >= 8)
         return 2;
     return 4;
+}
+
+/// Threads per CTA the sweep kernel is compiled for (`__launch_bounds__`).
+template <typename Cell> constexpr int max_threads_per_cta() {
+    return (sizeof(Cell) > 64 && column_group_width<Cell>() == 1) ? 512 : 256;
 }
 
 /// Whether every plane of `Cell` can be staged by a TMA box load.
@@ -162,14 +176,14 @@ LaunchPlan make_plan(int device, unsigned grid_h, unsigned grid_w, std::size_t n
     unsigned block_x = unsigned(env_long("STST_BLOCK_X", 0));
     if (block_x == 0) {
         // 256 staged columns for small cells, narrower tiles once a cell is tens of bytes wide.
-        block_x = sizeof(Cell) <= 16 ? 64 : 32;
+        block_x = (sizeof(Cell) <= 16 || cw == 1) ? 64 : 32;
         while (block_x > 32 && block_x * cw / 2 >= std::max(grid_w, 1u) + 2 * cw)
             block_x /= 2;
     }
     block_x = std::max(32u, block_x / 32 * 32);
     unsigned block_y = unsigned(env_long("STST_BLOCK_Y", 0));
     if (block_y == 0)
-        block_y = std::max(1u, 256u / block_x);
+        block_y = std::max(1u, unsigned(max_threads_per_cta<Cell>()) / block_x);
 
     if (fused_override == 0)
         fused_override = unsigned(env_long("STST_FUSE", 0));
@@ -218,20 +232,24 @@ LaunchPlan make_plan(int device, unsigned grid_h, unsigned grid_w, std::size_t n
         const double hbm_bytes = 2.0 * double(sizeof(Cell)) * n_sub; // one read + one write / sweep
         const double onchip = 0.55 * double(sizeof(Cell)) * n_sub + 1.0 * n_sub;
         double best_cost = 0.0;
-        // Tiles that waste most of their footprint on halo are not considered, unless (tiny grids)
-        // nothing else exists.
+        // Candidates: every depth k, with the shared memory of an SM split between `ctas_per_sm`
+        // co-resident CTAs (one CTA's staging overlaps the other's sweeps) or given to a single CTA
+        // (taller tiles, less halo overhead — what fat cells need). Tiles that waste most of their
+        // footprint on halo are not considered, unless (tiny grids) nothing else exists.
         for (double min_efficiency : {0.35, 0.0}) {
-            for (unsigned k = 1; k <= k_cap; k++) {
-                TileShape s = evaluate(k, ctas_per_sm);
-                if (!s.feasible)
-                    s = evaluate(k, 1);
-                if (!s.feasible || s.efficiency < min_efficiency)
-                    continue;
-                const double cost = std::max(hbm_bytes / k, onchip) / s.efficiency;
-                if (best_k == 0 || cost < best_cost * 0.97) {
-                    best_k = k;
-                    best = s;
-                    best_cost = cost;
+            for (unsigned ctas : {ctas_per_sm, 1u}) {
+                for (unsigned k = 1; k <= k_cap; k++) {
+                    const TileShape s = evaluate(k, ctas);
+                    if (!s.feasible || s.efficiency < min_efficiency)
+                        continue;
+                    // a lone CTA per SM cannot hide its own staging and barriers: 25 % handicap
+                    const double solo = (ctas == 1 && ctas_per_sm > 1) ? 1.25 : 1.0;
+                    const double cost = solo * std::max(hbm_bytes / k, onchip) / s.efficiency;
+                    if (best_k == 0 || cost < best_cost * 0.97) {
+                        best_k = k;
+                        best = s;
+                        best_cost = cost;
+                    }
                 }
             }
             if (best_k != 0)

@@ -207,14 +207,22 @@ template <typename F> class SlabUpdate {
 
     /// Replace the owned rows by `cells` (dense row-major array of whole cells, owned_rows x width).
     /// Asynchronous on stream(); `cells` should be pinned and must stay valid until synchronize().
-    void upload(const Cell *cells) {
-        transfer</*to_device=*/true>(const_cast<Cell *>(cells));
+    void upload(const Cell *cells) { upload_rows(cells, 0, owned_rows()); }
+
+    /// Replace `n_rows` owned rows starting at slab-local row `first_row` (for slabs too large to be
+    /// staged in host memory at once).
+    void upload_rows(const Cell *cells, std::size_t first_row, std::size_t n_rows) {
+        check_row_range(first_row, n_rows);
+        transfer</*to_device=*/true>(const_cast<Cell *>(cells), first_row, n_rows);
     }
 
     /// Copy the owned rows of the current generation into `cells`. Returns after the copy is done.
-    void download(Cell *cells) {
+    void download(Cell *cells) { download_rows(cells, 0, owned_rows()); }
+
+    void download_rows(Cell *cells, std::size_t first_row, std::size_t n_rows) {
+        check_row_range(first_row, n_rows);
         join_streams();
-        transfer</*to_device=*/false>(cells);
+        transfer</*to_device=*/false>(cells, first_row, n_rows);
         STST_RT_CHECK(stst_stream_synchronize(interior_stream));
     }
 
@@ -396,20 +404,28 @@ template <typename F> class SlabUpdate {
         epoch++;
     }
 
-    template <bool to_device> void transfer(Cell *cells) {
+    void check_row_range(std::size_t first_row, std::size_t n_rows) const {
+        if (first_row > owned_rows() || n_rows > owned_rows() - first_row)
+            throw std::range_error("StencilStream-B200: row range exceeds the slab");
+    }
+
+    template <bool to_device>
+    void transfer(Cell *cells, std::size_t first_row, std::size_t n_rows) {
 #if defined(__CUDACC__)
         select_device();
         const int cur = int(epoch & 1);
         PlaneSet planes = layout.planes(base, cur);
         const std::size_t width = cfg.grid_cols;
         const std::size_t row_bytes = std::max<std::size_t>(width * sizeof(Cell), 1);
+        if (n_rows == 0)
+            return;
         const std::size_t chunk_rows =
-            std::max<std::size_t>(1, std::min<std::size_t>(owned_rows(), (std::size_t(64) << 20) / row_bytes));
+            std::max<std::size_t>(1, std::min<std::size_t>(n_rows, (std::size_t(64) << 20) / row_bytes));
         void *staging[2] = {device_alloc(cfg.device, chunk_rows * width * sizeof(Cell), interior_stream),
                             device_alloc(cfg.device, chunk_rows * width * sizeof(Cell), interior_stream)};
         std::size_t chunk = 0;
-        for (std::size_t row = 0; row < owned_rows(); row += chunk_rows, chunk++) {
-            const std::size_t rows = std::min(chunk_rows, owned_rows() - row);
+        for (std::size_t row = 0; row < n_rows; row += chunk_rows, chunk++) {
+            const std::size_t rows = std::min(chunk_rows, n_rows - row);
             const std::size_t n = rows * width;
             Cell *stage = static_cast<Cell *>(staging[chunk & 1]);
             const unsigned block = 256;
@@ -419,9 +435,11 @@ template <typename F> class SlabUpdate {
             if constexpr (to_device) {
                 STST_RT_CHECK(stst_memcpy_h2d_async(stage, cells + row * width, n * sizeof(Cell),
                                                     interior_stream));
-                scatter_cells_kernel<Cell><<<grid, block, 0, s>>>(stage, planes, width, ghost + row, n);
+                scatter_cells_kernel<Cell><<<grid, block, 0, s>>>(stage, planes, width,
+                                                                  ghost + first_row + row, n);
             } else {
-                gather_cells_kernel<Cell><<<grid, block, 0, s>>>(stage, planes, width, ghost + row, n);
+                gather_cells_kernel<Cell><<<grid, block, 0, s>>>(stage, planes, width,
+                                                                 ghost + first_row + row, n);
                 STST_RT_CHECK(stst_memcpy_d2h_async(cells + row * width, stage, n * sizeof(Cell),
                                                     interior_stream));
             }

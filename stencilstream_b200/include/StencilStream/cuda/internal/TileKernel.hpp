@@ -43,6 +43,9 @@ namespace stencil {
 namespace cuda {
 namespace internal {
 
+/// Neighbourhood acquisition strategies of sweep_rows.
+inline constexpr int window_shift = 0, window_rotate = 1, window_reload = 2;
+
 /// Upper bound for the number of iterations fused into one launch (sizes the TDV parameter array).
 inline constexpr unsigned max_fused_iterations = 16;
 
@@ -345,10 +348,17 @@ __device__ __forceinline__ void stage_tile(TileView<Cell> const &tile, PlaneSet 
  * Apply sub-iteration `SUB` of `tf` to tile rows [row_lo, row_hi) of `in`, writing either into the
  * tile buffer `out` or — if `to_global` — into the destination planes in HBM.
  *
- * \tparam kRotate Unroll the row loop (2r+1)-fold so that the register window rotates by renaming
- *                 instead of by moves. Pays off for light functors, bloats code for heavy ones.
+ * \tparam kMode How a thread obtains the (2r+1) x (CW+2r) neighbourhood of its column group:
+ *               window_shift  — keep it in registers, load one new row per step, shift by moves;
+ *               window_rotate — same, but the row loop is unrolled (2r+1)-fold so that the window
+ *                               rotates by register renaming (light-weight cells only: code size);
+ *               window_reload — re-read all (2r+1) rows from shared memory for every output row, with
+ *                               plain loads instead of shuffles. Nothing stays live between rows, so
+ *                               only fields the functor really reads cost registers and loads: the
+ *                               choice for fat cells (tens of bytes), where a resident window of whole
+ *                               cells exceeds the register file.
  */
-template <typename F, int CW, bool kInterior, bool kRotate, std::size_t SUB>
+template <typename F, int CW, bool kInterior, int kMode, std::size_t SUB>
 __device__ __forceinline__ void
 sweep_rows(F const &tf, typename F::Cell const &halo_value,
            typename F::TimeDependentValue const &tdv, std::size_t iteration,
@@ -368,10 +378,11 @@ sweep_rows(F const &tf, typename F::Cell const &halo_value,
     const int c0 = int(threadIdx.x) * CW;
     const int lane = int(threadIdx.x) & 31;
 
-    // Split the rows of this sweep evenly over the blockDim.y row groups (uniform per warp).
-    const int per_group = (row_hi - row_lo + int(blockDim.y) - 1) / int(blockDim.y);
-    const int y_begin = row_lo + int(threadIdx.y) * per_group;
-    const int y_end = min(y_begin + per_group, row_hi);
+    // Split the rows of this sweep over the blockDim.y row groups (uniform per warp), balanced to
+    // within one row: group g gets rows [n*g/G, n*(g+1)/G).
+    const int n_rows = row_hi - row_lo;
+    const int y_begin = row_lo + (n_rows * int(threadIdx.y)) / int(blockDim.y);
+    const int y_end = row_lo + (n_rows * (int(threadIdx.y) + 1)) / int(blockDim.y);
     if (y_begin >= y_end)
         return;
 
@@ -389,7 +400,7 @@ sweep_rows(F const &tf, typename F::Cell const &halo_value,
 #pragma unroll
             for (int j = 1; j <= R; j++) {
                 T left, right;
-                if constexpr (is_shuffleable_v<T>) {
+                if constexpr (is_shuffleable_v<T> && kMode != window_reload) {
                     left = shuffle_from_lower_lane(p.v[CW - j]);
                     right = shuffle_from_upper_lane(p.v[j - 1]);
                     if (lane == 0)
@@ -484,11 +495,20 @@ sweep_rows(F const &tf, typename F::Cell const &halo_value,
     };
 
     // Prime the window with the D-1 rows above/around the first row.
+    if constexpr (kMode != window_reload) {
 #pragma unroll
-    for (int j = 0; j < D - 1; j++)
-        load_row(win[j], y_begin - R + j);
+        for (int j = 0; j < D - 1; j++)
+            load_row(win[j], y_begin - R + j);
+    }
 
-    if constexpr (kRotate) {
+    if constexpr (kMode == window_reload) {
+        for (int y = y_begin; y < y_end; y++) {
+#pragma unroll
+            for (int j = 0; j < D; j++)
+                load_row(win[j], y - R + j);
+            compute_row(std::integral_constant<int, 0>{}, y);
+        }
+    } else if constexpr (kMode == window_rotate) {
         for (int y = y_begin; y < y_end; y += D) {
             [&]<int... Us>(std::integer_sequence<int, Us...>) {
                 (
@@ -519,7 +539,7 @@ sweep_rows(F const &tf, typename F::Cell const &halo_value,
 // one tile: stage, run all fused sweeps, write back
 // ------------------------------------------------------------------------------------------------
 
-template <typename F, int CW, bool kInterior, bool kRotate>
+template <typename F, int CW, bool kInterior, int kMode>
 __device__ __forceinline__ void
 run_tile(F const &tf, typename F::Cell const &halo_value,
          TdvArray<typename F::TimeDependentValue> const &tdvs, PlaneSet const &src,
@@ -551,7 +571,7 @@ run_tile(F const &tf, typename F::Cell const &halo_value,
                     const int hi = int(rows) - int(step + 1) * R;
                     TileView<Cell> const &in = (step & 1u) ? buf1 : buf0;
                     TileView<Cell> const &out = (step & 1u) ? buf0 : buf1;
-                    sweep_rows<F, CW, kInterior, kRotate, Subs>(tf, halo_value, tdv, iteration, in,
+                    sweep_rows<F, CW, kInterior, kMode, Subs>(tf, halo_value, tdv, iteration, in,
                                                                 out, last, dst, push, geo, gy0,
                                                                 gx0, lo, hi);
                     if (!last)
@@ -568,7 +588,7 @@ run_tile(F const &tf, typename F::Cell const &halo_value,
  * block: (TWH / CW, row groups), blockDim.x a multiple of 32.
  * Dynamic shared memory: two tile buffers (one if the launch consists of a single sweep).
  */
-template <typename F, int CW, bool kRotate, int kMaxThreads, int kMinBlocks>
+template <typename F, int CW, int kMode, int kMaxThreads, int kMinBlocks>
 __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
     fused_sweep_kernel(const __grid_constant__ F tf,
                        const __grid_constant__ typename F::Cell halo_value,
@@ -600,10 +620,10 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
                           tile_gx + int(geo.tile_w + geo.hpad) <= int(geo.grid_w);
 
     if (interior) {
-        run_tile<F, CW, true, kRotate>(tf, halo_value, tdvs, src, dst, push, maps, geo, smem, &mbar,
+        run_tile<F, CW, true, kMode>(tf, halo_value, tdvs, src, dst, push, maps, geo, smem, &mbar,
                                        gy0, gx0);
     } else {
-        run_tile<F, CW, false, false>(tf, halo_value, tdvs, src, dst, push, maps, geo, smem, &mbar,
+        run_tile<F, CW, false, (kMode == window_reload ? window_reload : window_shift)>(tf, halo_value, tdvs, src, dst, push, maps, geo, smem, &mbar,
                                       gy0, gx0);
     }
 }

@@ -58,6 +58,8 @@ def _slab_lib(strict: bool | None = None):
         lib.stst_slab_attach_local.argtypes = [vp, C.c_int, vp]
         lib.stst_slab_copy_from_host.argtypes = [vp, vp, C.c_size_t]
         lib.stst_slab_copy_to_host.argtypes = [vp, vp, C.c_size_t]
+        lib.stst_slab_copy_rows_from_host.argtypes = [vp, C.c_size_t, C.c_size_t, vp, C.c_size_t]
+        lib.stst_slab_copy_rows_to_host.argtypes = [vp, C.c_size_t, C.c_size_t, vp, C.c_size_t]
         lib.stst_slab_exchange_halos.argtypes = [vp]
         lib.stst_slab_update.argtypes = [vp, C.POINTER(_native.UpdateParams)]
         lib.stst_slab_synchronize.argtypes = [vp]
@@ -117,6 +119,19 @@ class NativeSlab:
             raise ValueError("copy_to_host needs a C-contiguous array of the workload's cell dtype")
         _check(self._lib, self._lib.stst_slab_copy_to_host(
             self._handle, out.ctypes.data_as(C.c_void_p), out.nbytes))
+
+    def copy_rows_from_host(self, first_row: int, cells: np.ndarray) -> None:
+        """Replace the owned rows [first_row, first_row + len(cells)) (slab-local indices)."""
+        arr = np.ascontiguousarray(cells, dtype=self.dtype)
+        _check(self._lib, self._lib.stst_slab_copy_rows_from_host(
+            self._handle, first_row, arr.shape[0], arr.ctypes.data_as(C.c_void_p), arr.nbytes))
+        self.synchronize()  # `arr` may be a temporary
+
+    def copy_rows_to_host(self, first_row: int, out: np.ndarray) -> None:
+        if out.dtype != self.dtype or not out.flags["C_CONTIGUOUS"]:
+            raise ValueError("copy_rows_to_host needs a C-contiguous array of the cell dtype")
+        _check(self._lib, self._lib.stst_slab_copy_rows_to_host(
+            self._handle, first_row, out.shape[0], out.ctypes.data_as(C.c_void_p), out.nbytes))
 
     def exchange_halos(self) -> None:
         _check(self._lib, self._lib.stst_slab_exchange_halos(self._handle))
@@ -191,6 +206,14 @@ class ShardedStencilUpdate:
             from .api import RangeError
             raise RangeError("The target buffer has not the same size as the slab")
         self.slab.copy_from_host(cells)
+        self.slab.exchange_halos()
+
+    def load_chunks(self, generate, chunk_rows: int = 256) -> None:
+        """`load()` for slabs that should not be staged on the host at once: `generate(lo, hi)` returns
+        the cells of the GLOBAL rows [lo, hi), which are uploaded chunk by chunk. Collective."""
+        for lo in range(self.row_lo, self.row_hi, chunk_rows):
+            hi = min(lo + chunk_rows, self.row_hi)
+            self.slab.copy_rows_from_host(lo - self.row_lo, generate(lo, hi))
         self.slab.exchange_halos()
 
     def to_numpy(self, out: np.ndarray | None = None) -> np.ndarray:
