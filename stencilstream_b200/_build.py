@@ -102,6 +102,16 @@ def build_workloads(strict: bool = False, force: bool = False, verbose: bool = F
     return target
 
 
+def build_variant(tag: str, extra_flags, verbose: bool = False) -> Path:
+    """An experimental build of the workloads library with extra nvcc flags (tuning only):
+    stencilstream_b200/libstst_workloads_<tag>.so, selected at run time by STST_WORKLOADS_LIB."""
+    build_runtime(verbose=verbose)
+    target = PKG / f"libstst_workloads_{tag}.so"
+    _run([_nvcc(), *NVCC_COMMON, *ARCH_FLAGS, *extra_flags, PKG / "csrc" / "workloads.cu", "-o", target,
+          f"-L{PKG}", "-lstst_rt", "-Xlinker", "-rpath,$ORIGIN"], verbose)
+    return target
+
+
 def build_oracle_port(force: bool = False, verbose: bool = False) -> Path:
     target = ORACLE / "liboracle_port.so"
     inputs = [ORACLE / "stencil_oracle.c", ROOT / "include" / "stst_workloads.h"]

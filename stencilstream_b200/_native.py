@@ -189,7 +189,10 @@ def workloads_lib(strict: bool | None = None):
     key = "wl_strict" if strict else "wl"
     if key not in _libs:
         runtime_lib()
-        lib = _load(PKG / ("libstst_workloads_strict.so" if strict else "libstst_workloads.so"))
+        name = "libstst_workloads_strict.so" if strict else "libstst_workloads.so"
+        if not strict and os.environ.get("STST_WORKLOADS_LIB"):
+            name = os.environ["STST_WORKLOADS_LIB"]  # an experimental build (see _build.build_variant)
+        lib = _load(PKG / name)
         vp = C.c_void_p
         lib.stst_workloads_last_error.restype = C.c_char_p
         lib.stst_workload_name.restype = C.c_char_p

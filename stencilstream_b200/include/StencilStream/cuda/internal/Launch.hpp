@@ -125,8 +125,7 @@ template <typename F> struct SweepLauncher {
 
         const unsigned rows = geo.tile_h + 2 * geo.halo;
         const unsigned cols = plan.block_x * unsigned(CW);
-        const std::size_t smem =
-            tile_buffer_bytes<Cell>(rows, cols) * ((n_gens * n_sub > 1) ? 2 : 1);
+        const std::size_t smem = tile_smem_bytes<Cell>(rows, cols, (n_gens * n_sub > 1) ? 2 : 1);
 
         static const TensorMapSet no_maps{};
         TensorMapSet const *maps = &no_maps;

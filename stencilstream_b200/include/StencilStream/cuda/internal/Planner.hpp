@@ -72,6 +72,10 @@ template <typename Cell> constexpr int column_group_width() {
         return 1;
     if (widest >= 8)
         return 2;
+#if defined(STST_LIGHT_COLUMN_GROUP_WIDTH)
+    if (sizeof(Cell) <= 8 && widest == 4)
+        return STST_LIGHT_COLUMN_GROUP_WIDTH;
+#endif
     return 4;
 }
 
@@ -145,7 +149,7 @@ TileShape shape_for(unsigned k, unsigned n_sub, unsigned radius, unsigned cw, un
     tile_h = std::min(tile_h, std::max(grid_h, 1u));
     s.tile_h = tile_h;
     s.rows = tile_h + 2 * s.halo;
-    s.smem_bytes = tile_buffer_bytes<Cell>(s.rows, s.cols) * n_buffers;
+    s.smem_bytes = tile_smem_bytes<Cell>(s.rows, s.cols, n_buffers);
     s.efficiency = double(s.tile_h) * s.tile_w / (double(s.rows) * s.cols);
     s.feasible = s.smem_bytes <= smem_budget;
     return s;
@@ -177,6 +181,8 @@ LaunchPlan make_plan(int device, unsigned grid_h, unsigned grid_w, std::size_t n
     if (block_x == 0) {
         // 256 staged columns for small cells, narrower tiles once a cell is tens of bytes wide.
         block_x = (sizeof(Cell) <= 16 || cw == 1) ? 64 : 32;
+        if (cw > 4)
+            block_x = 32;
         while (block_x > 32 && block_x * cw / 2 >= std::max(grid_w, 1u) + 2 * cw)
             block_x /= 2;
     }
@@ -230,7 +236,8 @@ LaunchPlan make_plan(int device, unsigned grid_h, unsigned grid_w, std::size_t n
     } else {
         // Cost model in "HBM-byte equivalents" per cell-iteration.
         const double hbm_bytes = 2.0 * double(sizeof(Cell)) * n_sub; // one read + one write / sweep
-        const double onchip = 0.55 * double(sizeof(Cell)) * n_sub + 1.0 * n_sub;
+        // on-chip work per cell-iteration, fitted to measured sweeps (profiles/r01_sweep_*.log)
+        const double onchip = 0.475 * double(sizeof(Cell)) * n_sub + 0.4 * n_sub;
         double best_cost = 0.0;
         // Candidates: every depth k, with the shared memory of an SM split between `ctas_per_sm`
         // co-resident CTAs (one CTA's staging overlaps the other's sweeps) or given to a single CTA

@@ -21,9 +21,10 @@
  *   3. The last sweep writes its CW-wide column groups straight to HBM with 128-bit stores.
  *
  * Inside a sweep a thread owns CW adjacent columns and walks down a run of rows, holding the
- * (2r+1) x (CW+2r) window in registers: per row it issues one vector shared-memory load per plane,
- * takes the 2r edge columns from its warp neighbours with shuffles, builds the user-visible
- * `Stencil` objects in registers and calls the transition function CW times. Loads of neighbour
+ * (2r+1) x (CW+2r) window in registers: per row it issues one vector shared-memory load per plane
+ * plus 2r scalar loads for the edge columns (warp shuffles are the compile-time alternative; they
+ * measured slower, see load_row), builds the user-visible `Stencil` objects in registers and calls
+ * the transition function CW times. Loads of neighbour
  * fields the functor never reads are dead code and disappear.
  *
  * Tiles whose halo-extended footprint lies completely inside the grid take a path without any
@@ -42,6 +43,10 @@
 namespace stencil {
 namespace cuda {
 namespace internal {
+
+/// Where sweep_rows writes: known at compile time (two specialised loop bodies, light functors) or
+/// decided by its run-time argument (one body, heavy functors: code size).
+inline constexpr int store_tile = 0, store_grid = 1, store_runtime = 2;
 
 /// Neighbourhood acquisition strategies of sweep_rows.
 inline constexpr int window_shift = 0, window_rotate = 1, window_reload = 2;
@@ -219,6 +224,11 @@ __device__ __forceinline__ void tma_load_2d(void *smem_dst, const void *tensor_m
 // shared-memory tile bookkeeping
 // ------------------------------------------------------------------------------------------------
 
+/// Unused bytes in front of the first and behind the last tile buffer: edge-column loads of the
+/// first/last thread of a tile row reach up to `radius` elements beyond their row, and must stay
+/// inside the CTA's dynamic shared memory (what they fetch there is never used for exact cells).
+inline constexpr unsigned tile_guard_bytes = 128;
+
 /// Bytes of one tile buffer (all planes, each plane padded to 128 bytes).
 template <typename Cell>
 STST_HD inline std::size_t tile_buffer_bytes(unsigned tile_rows, unsigned tile_cols) {
@@ -229,6 +239,13 @@ STST_HD inline std::size_t tile_buffer_bytes(unsigned tile_rows, unsigned tile_c
         total += (b + 127) / 128 * 128;
     }
     return total;
+}
+
+/// Dynamic shared memory of a CTA: guard, `n_buffers` tile buffers, guard.
+template <typename Cell>
+STST_HD inline std::size_t tile_smem_bytes(unsigned tile_rows, unsigned tile_cols,
+                                           unsigned n_buffers) {
+    return tile_buffer_bytes<Cell>(tile_rows, tile_cols) * n_buffers + 2 * tile_guard_bytes;
 }
 
 template <typename Cell> struct TileView {
@@ -358,12 +375,12 @@ __device__ __forceinline__ void stage_tile(TileView<Cell> const &tile, PlaneSet 
  *                               choice for fat cells (tens of bytes), where a resident window of whole
  *                               cells exceeds the register file.
  */
-template <typename F, int CW, bool kInterior, int kMode, std::size_t SUB>
+template <typename F, int CW, bool kInterior, int kMode, int kStore, std::size_t SUB>
 __device__ __forceinline__ void
 sweep_rows(F const &tf, typename F::Cell const &halo_value,
            typename F::TimeDependentValue const &tdv, std::size_t iteration,
            TileView<typename F::Cell> const &in, TileView<typename F::Cell> const &out,
-           bool to_global, PlaneSet const &dst, HaloPush const &push, SweepGeometry const &geo,
+           bool to_global_arg, PlaneSet const &dst, HaloPush const &push, SweepGeometry const &geo,
            int gy0, int gx0, int row_lo, int row_hi) {
     using Cell = typename F::Cell;
     using TDV = typename F::TimeDependentValue;
@@ -377,6 +394,7 @@ sweep_rows(F const &tf, typename F::Cell const &halo_value,
     const int cols = int(in.cols);
     const int c0 = int(threadIdx.x) * CW;
     const int lane = int(threadIdx.x) & 31;
+    const bool to_global = kStore == store_runtime ? to_global_arg : (kStore == store_grid);
 
     // Split the rows of this sweep over the blockDim.y row groups (uniform per warp), balanced to
     // within one row: group g gets rows [n*g/G, n*(g+1)/G).
@@ -400,16 +418,29 @@ sweep_rows(F const &tf, typename F::Cell const &halo_value,
 #pragma unroll
             for (int j = 1; j <= R; j++) {
                 T left, right;
-                if constexpr (is_shuffleable_v<T> && kMode != window_reload) {
+                // The 2r edge columns of a thread's window belong to its lane neighbours. They can be
+                // fetched by warp shuffle (plus a load for the first/last lane of the warp) or by two
+                // plain scalar shared-memory loads at constant offsets from the vector load's address.
+                // Measured on B200 (profiles/r01_variants_shuffle_vs_lds_cw4_vs_cw8.log): the plain
+                // loads win by 17-20 % (Jacobi k=4 1154 -> 1378, HotSpot 548 -> 639 GCell-updates/s) —
+                // a shuffle occupies the same MIO issue slot as an LDS, and the shuffle variant needs
+                // the predicated fix-up loads on top. Define STST_EDGE_SHUFFLES for the shuffle variant.
+#if defined(STST_EDGE_SHUFFLES)
+                constexpr bool use_shuffles = true;
+#else
+                constexpr bool use_shuffles = false;
+#endif
+                if constexpr (is_shuffleable_v<T> && kMode != window_reload && use_shuffles) {
                     left = shuffle_from_lower_lane(p.v[CW - j]);
                     right = shuffle_from_upper_lane(p.v[j - 1]);
                     if (lane == 0)
-                        left = rp[max(c0 - j, 0)];
+                        left = rp[c0 - j];
                     if (lane == 31)
-                        right = rp[min(c0 + CW - 1 + j, cols - 1)];
+                        right = rp[c0 + CW - 1 + j];
                 } else {
-                    left = rp[max(c0 - j, 0)];
-                    right = rp[min(c0 + CW - 1 + j, cols - 1)];
+                    // constant offsets from the vector load's address; see tile_guard_bytes
+                    left = rp[c0 - j];
+                    right = rp[c0 + CW - 1 + j];
                 }
                 L::template get<I>(w[R - j]) = left;
                 L::template get<I>(w[R + CW - 1 + j]) = right;
@@ -554,8 +585,8 @@ run_tile(F const &tf, typename F::Cell const &halo_value,
     const unsigned cols = blockDim.x * CW;
     const unsigned buffer_bytes = unsigned(tile_buffer_bytes<Cell>(rows, cols));
 
-    TileView<Cell> buf0(smem, rows, cols);
-    TileView<Cell> buf1(smem + buffer_bytes, rows, cols);
+    TileView<Cell> buf0(smem + tile_guard_bytes, rows, cols);
+    TileView<Cell> buf1(smem + tile_guard_bytes + buffer_bytes, rows, cols);
 
     stage_tile<Cell, CW, kInterior>(buf0, src, maps, geo, halo_value, gy0, gx0, mbar);
 
@@ -571,9 +602,20 @@ run_tile(F const &tf, typename F::Cell const &halo_value,
                     const int hi = int(rows) - int(step + 1) * R;
                     TileView<Cell> const &in = (step & 1u) ? buf1 : buf0;
                     TileView<Cell> const &out = (step & 1u) ? buf0 : buf1;
-                    sweep_rows<F, CW, kInterior, kMode, Subs>(tf, halo_value, tdv, iteration, in,
-                                                                out, last, dst, push, geo, gy0,
-                                                                gx0, lo, hi);
+                    if constexpr (sizeof(Cell) <= 16) {
+                        if (last)
+                            sweep_rows<F, CW, kInterior, kMode, store_grid, Subs>(
+                                tf, halo_value, tdv, iteration, in, out, true, dst, push, geo, gy0,
+                                gx0, lo, hi);
+                        else
+                            sweep_rows<F, CW, kInterior, kMode, store_tile, Subs>(
+                                tf, halo_value, tdv, iteration, in, out, false, dst, push, geo, gy0,
+                                gx0, lo, hi);
+                    } else {
+                        sweep_rows<F, CW, kInterior, kMode, store_runtime, Subs>(
+                            tf, halo_value, tdv, iteration, in, out, last, dst, push, geo, gy0, gx0,
+                            lo, hi);
+                    }
                     if (!last)
                         __syncthreads();
                     step++;
