@@ -141,7 +141,7 @@ template <typename F> struct SweepLauncher {
                                          std::to_string(region.device));
         }
 
-        auto kernel = fused_sweep_kernel<F, CW, kMode, max_threads_per_cta<Cell>(), 1>;
+        auto kernel = fused_sweep_kernel<F, CW, kMode, fixed_block_x<Cell>(), max_threads_per_cta<Cell>(), 1>;
         static std::size_t configured_smem_per_device[64] = {};
         std::size_t &configured_smem = configured_smem_per_device[region.device & 63];
         if (smem > configured_smem) {

@@ -19,6 +19,7 @@
 #include "TileKernel.hpp"
 
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
 #include <stdexcept>
 #include <string>
@@ -81,7 +82,17 @@ template <typename Cell> constexpr int column_group_width() {
 
 /// Threads per CTA the sweep kernel is compiled for (`__launch_bounds__`).
 template <typename Cell> constexpr int max_threads_per_cta() {
+#if defined(STST_LIGHT_MAX_THREADS)
+    if (sizeof(Cell) <= 8)
+        return STST_LIGHT_MAX_THREADS;
+#endif
     return (sizeof(Cell) > 64 && column_group_width<Cell>() == 1) ? 512 : 256;
+}
+
+/// blockDim.x the sweep kernel is compiled for, or 0 if it is a run-time choice. Cells that use
+/// lane-major tiles (TileKernel.hpp) get a fixed 64 so that their sub-row offsets are immediates.
+template <typename Cell> constexpr int fixed_block_x() {
+    return lane_major_tiles<Cell, column_group_width<Cell>()>() ? 64 : 0;
 }
 
 /// Whether every plane of `Cell` can be staged by a TMA box load.
@@ -159,7 +170,7 @@ TileShape shape_for(unsigned k, unsigned n_sub, unsigned radius, unsigned cw, un
  * Plan launches for transition function `F` on `device`.
  *
  * The heuristic models the time per cell-iteration of a k-fused launch as
- *     max(HBM bytes / k, on-chip work) / efficiency
+ *     sqrt((HBM bytes / k)^2 + (on-chip work)^2) / efficiency
  * with on-chip work growing with the cell size, and picks the k that minimises it among the
  * feasible ones (at most `max_k`). Two CTAs per SM are targeted so that one CTA's tile staging
  * overlaps the other's sweeps.
@@ -187,9 +198,13 @@ LaunchPlan make_plan(int device, unsigned grid_h, unsigned grid_w, std::size_t n
             block_x /= 2;
     }
     block_x = std::max(32u, block_x / 32 * 32);
+    if (fixed_block_x<Cell>() != 0)
+        block_x = unsigned(fixed_block_x<Cell>());
     unsigned block_y = unsigned(env_long("STST_BLOCK_Y", 0));
     if (block_y == 0)
         block_y = std::max(1u, unsigned(max_threads_per_cta<Cell>()) / block_x);
+    if (block_x * block_y > unsigned(max_threads_per_cta<Cell>()))
+        throw std::invalid_argument("StencilStream-B200: CTA shape exceeds the compiled thread limit");
 
     if (fused_override == 0)
         fused_override = unsigned(env_long("STST_FUSE", 0));
@@ -249,10 +264,13 @@ LaunchPlan make_plan(int device, unsigned grid_h, unsigned grid_w, std::size_t n
                     const TileShape s = evaluate(k, ctas);
                     if (!s.feasible || s.efficiency < min_efficiency)
                         continue;
-                    // a lone CTA per SM cannot hide its own staging and barriers: 25 % handicap
-                    const double solo = (ctas == 1 && ctas_per_sm > 1) ? 1.25 : 1.0;
-                    const double cost = solo * std::max(hbm_bytes / k, onchip) / s.efficiency;
-                    if (best_k == 0 || cost < best_cost * 0.97) {
+                    // a lone CTA per SM cannot hide its own staging and barriers: measured 16-27 %
+                    // slower at equal k for light cells, hence a 40 % handicap in this model
+                    const double solo = (ctas == 1 && ctas_per_sm > 1) ? 1.40 : 1.0;
+                    // HBM time and on-chip time overlap only partly: 2-norm instead of max()
+                    const double hbm = hbm_bytes / k;
+                    const double cost = solo * std::sqrt(hbm * hbm + onchip * onchip) / s.efficiency;
+                    if (best_k == 0 || cost < best_cost * 0.995) {
                         best_k = k;
                         best = s;
                         best_cost = cost;

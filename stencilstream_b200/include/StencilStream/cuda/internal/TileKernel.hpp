@@ -48,6 +48,31 @@ namespace internal {
 /// decided by its run-time argument (one body, heavy functors: code size).
 inline constexpr int store_tile = 0, store_grid = 1, store_runtime = 2;
 
+/**
+ * Lane-major tile rows. In the natural (row-major) tile layout a thread's CW = 4 columns are one
+ * 128-bit vector, which is ideal for the vector load, but the two edge columns it needs from its
+ * neighbours sit 16 bytes apart from lane to lane: a 4-way bank conflict, 4 wavefronts per scalar
+ * load — after all other savings, half of the kernel's shared-memory traffic (ncu: 44 % of the
+ * wavefronts were conflicts, the MIO pipe 77 % busy). In the lane-major layout tile row y of a plane is
+ * stored as CW sub-rows of TX = blockDim.x elements, column c at `y*cols + (c % CW)*TX + c / CW`, so
+ * that lane t finds its own columns at t, TX+t, 2TX+t, 3TX+t and its neighbours' edge columns at
+ * 3TX+t-1 and t+1: every access is a conflict-free scalar load (10 instead of 16 wavefronts per
+ * warp and row). TMA delivers tiles in natural order, so the first sweep of a launch reads natural and
+ * writes lane-major; all later sweeps read and write lane-major. The price is scalar instead of vector
+ * loads/stores (6 + 4 instead of 3 + 1 instructions per row and plane), so it pays where shared memory,
+ * not instruction issue, is the limit: measured +8..12 % for Jacobi (one 4-byte plane; k=6: 1603
+ * GCell-updates/s) but -4 % for HotSpot (two planes, only one of which is read at neighbours) —
+ * profiles/r01_sweep_light_v4_lane_major.log. Hence: scalar 4-byte cells only.
+ */
+template <typename Cell, int CW> constexpr bool lane_major_tiles() {
+#if defined(STST_NO_LANE_MAJOR)
+    return false;
+#else
+    using L = CellLayout<Cell>;
+    return CW == 4 && L::n_planes == 1 && L::plane_bytes(0) == 4;
+#endif
+}
+
 /// Neighbourhood acquisition strategies of sweep_rows.
 inline constexpr int window_shift = 0, window_rotate = 1, window_reload = 2;
 
@@ -375,7 +400,8 @@ __device__ __forceinline__ void stage_tile(TileView<Cell> const &tile, PlaneSet 
  *                               choice for fat cells (tens of bytes), where a resident window of whole
  *                               cells exceeds the register file.
  */
-template <typename F, int CW, bool kInterior, int kMode, int kStore, std::size_t SUB>
+template <typename F, int CW, bool kInterior, int kMode, int kStore, bool kInLaneMajor,
+          bool kOutLaneMajor, int kTX, std::size_t SUB>
 __device__ __forceinline__ void
 sweep_rows(F const &tf, typename F::Cell const &halo_value,
            typename F::TimeDependentValue const &tdv, std::size_t iteration,
@@ -394,6 +420,8 @@ sweep_rows(F const &tf, typename F::Cell const &halo_value,
     const int cols = int(in.cols);
     const int c0 = int(threadIdx.x) * CW;
     const int lane = int(threadIdx.x) & 31;
+    // kTX != 0: blockDim.x is known at compile time, lane-major offsets become immediates
+    const int tx = int(threadIdx.x), TX = kTX ? kTX : int(blockDim.x);
     const bool to_global = kStore == store_runtime ? to_global_arg : (kStore == store_grid);
 
     // Split the rows of this sweep over the blockDim.y row groups (uniform per warp), balanced to
@@ -411,6 +439,19 @@ sweep_rows(F const &tf, typename F::Cell const &halo_value,
         for_each_plane<Cell>([&](auto I) {
             using T = typename L::template plane_t<I>;
             const T *rp = in.template plane<I>() + row * cols;
+            if constexpr (kInLaneMajor) {
+                // see lane_major_tiles(): all conflict-free scalar loads
+                const T *q = rp + tx;
+#pragma unroll
+                for (int i = 0; i < CW; i++)
+                    L::template get<I>(w[R + i]) = q[i * TX];
+#pragma unroll
+                for (int j = 1; j <= R; j++) {
+                    L::template get<I>(w[R - j]) = q[(CW - j) * TX - 1];
+                    L::template get<I>(w[R + CW - 1 + j]) = q[(j - 1) * TX + 1];
+                }
+                return;
+            }
             const Pack<T, CW> p = *reinterpret_cast<const Pack<T, CW> *>(rp + c0);
 #pragma unroll
             for (int i = 0; i < CW; i++)
@@ -479,11 +520,18 @@ sweep_rows(F const &tf, typename F::Cell const &halo_value,
         if (!to_global) {
             for_each_plane<Cell>([&](auto I) {
                 using T = typename L::template plane_t<I>;
-                Pack<T, CW> q;
+                if constexpr (kOutLaneMajor) {
+                    T *o = out.template plane<I>() + y * cols + tx;
 #pragma unroll
-                for (int i = 0; i < CW; i++)
-                    q.v[i] = L::template get<I>(result[i]);
-                *reinterpret_cast<Pack<T, CW> *>(out.template plane<I>() + y * cols + c0) = q;
+                    for (int i = 0; i < CW; i++)
+                        o[i * TX] = L::template get<I>(result[i]);
+                } else {
+                    Pack<T, CW> q;
+#pragma unroll
+                    for (int i = 0; i < CW; i++)
+                        q.v[i] = L::template get<I>(result[i]);
+                    *reinterpret_cast<Pack<T, CW> *>(out.template plane<I>() + y * cols + c0) = q;
+                }
             });
         } else {
             // Only the tile's own column groups are exact after the last sweep.
@@ -570,7 +618,7 @@ sweep_rows(F const &tf, typename F::Cell const &halo_value,
 // one tile: stage, run all fused sweeps, write back
 // ------------------------------------------------------------------------------------------------
 
-template <typename F, int CW, bool kInterior, int kMode>
+template <typename F, int CW, bool kInterior, int kMode, int kTX>
 __device__ __forceinline__ void
 run_tile(F const &tf, typename F::Cell const &halo_value,
          TdvArray<typename F::TimeDependentValue> const &tdvs, PlaneSet const &src,
@@ -602,19 +650,39 @@ run_tile(F const &tf, typename F::Cell const &halo_value,
                     const int hi = int(rows) - int(step + 1) * R;
                     TileView<Cell> const &in = (step & 1u) ? buf1 : buf0;
                     TileView<Cell> const &out = (step & 1u) ? buf0 : buf1;
-                    if constexpr (sizeof(Cell) <= 16) {
-                        if (last)
-                            sweep_rows<F, CW, kInterior, kMode, store_grid, Subs>(
-                                tf, halo_value, tdv, iteration, in, out, true, dst, push, geo, gy0,
-                                gx0, lo, hi);
-                        else
-                            sweep_rows<F, CW, kInterior, kMode, store_tile, Subs>(
-                                tf, halo_value, tdv, iteration, in, out, false, dst, push, geo, gy0,
-                                gx0, lo, hi);
-                    } else {
-                        sweep_rows<F, CW, kInterior, kMode, store_runtime, Subs>(
+                    constexpr bool kLM = lane_major_tiles<Cell, CW>() && kMode != window_reload;
+                    constexpr std::size_t kSub = Subs;
+                    auto sweep = [&](auto store_c, auto in_lm_c, auto out_lm_c) {
+                        sweep_rows<F, CW, kInterior, kMode, decltype(store_c)::value,
+                                   decltype(in_lm_c)::value, decltype(out_lm_c)::value, kTX, kSub>(
                             tf, halo_value, tdv, iteration, in, out, last, dst, push, geo, gy0, gx0,
                             lo, hi);
+                    };
+                    using std::false_type;
+                    using std::true_type;
+                    using grid_c = std::integral_constant<int, store_grid>;
+                    using tile_c = std::integral_constant<int, store_tile>;
+                    using runtime_c = std::integral_constant<int, store_runtime>;
+                    if constexpr (kLM) {
+                        // first sweep reads the TMA-staged (natural) tile, later ones lane-major tiles
+                        if (step == 0) {
+                            if (last)
+                                sweep(grid_c{}, false_type{}, false_type{});
+                            else
+                                sweep(tile_c{}, false_type{}, true_type{});
+                        } else {
+                            if (last)
+                                sweep(grid_c{}, true_type{}, false_type{});
+                            else
+                                sweep(tile_c{}, true_type{}, true_type{});
+                        }
+                    } else if constexpr (sizeof(Cell) <= 16) {
+                        if (last)
+                            sweep(grid_c{}, false_type{}, false_type{});
+                        else
+                            sweep(tile_c{}, false_type{}, false_type{});
+                    } else {
+                        sweep(runtime_c{}, false_type{}, false_type{});
                     }
                     if (!last)
                         __syncthreads();
@@ -630,7 +698,7 @@ run_tile(F const &tf, typename F::Cell const &halo_value,
  * block: (TWH / CW, row groups), blockDim.x a multiple of 32.
  * Dynamic shared memory: two tile buffers (one if the launch consists of a single sweep).
  */
-template <typename F, int CW, int kMode, int kMaxThreads, int kMinBlocks>
+template <typename F, int CW, int kMode, int kTX, int kMaxThreads, int kMinBlocks>
 __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
     fused_sweep_kernel(const __grid_constant__ F tf,
                        const __grid_constant__ typename F::Cell halo_value,
@@ -662,10 +730,10 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
                           tile_gx + int(geo.tile_w + geo.hpad) <= int(geo.grid_w);
 
     if (interior) {
-        run_tile<F, CW, true, kMode>(tf, halo_value, tdvs, src, dst, push, maps, geo, smem, &mbar,
+        run_tile<F, CW, true, kMode, kTX>(tf, halo_value, tdvs, src, dst, push, maps, geo, smem, &mbar,
                                        gy0, gx0);
     } else {
-        run_tile<F, CW, false, (kMode == window_reload ? window_reload : window_shift)>(tf, halo_value, tdvs, src, dst, push, maps, geo, smem, &mbar,
+        run_tile<F, CW, false, (kMode == window_reload ? window_reload : window_shift), kTX>(tf, halo_value, tdvs, src, dst, push, maps, geo, smem, &mbar,
                                       gy0, gx0);
     }
 }
