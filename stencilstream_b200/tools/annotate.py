@@ -8,7 +8,8 @@ the user's sources in the build tree:
     (= `__host__ __device__` under nvcc, nothing under a host compiler),
 
 which covers the transition function's `operator()` and helpers that receive the stencil (e.g. the
-FDTD material resolvers' `get_material_coefficients`). Nothing else is touched; constructors and
+FDTD material resolvers' `get_material_coefficients`). Helpers that do not take the stencil but are
+called from device code have to be named (`--also halo`). Nothing else is touched; constructors and
 `get_time_dependent_value` stay host-only (the latter is evaluated on the host, reference
 StencilStream/cuda/StencilUpdate.hpp:224). The sources under version control remain unmodified —
 include path and CMake target stay the only hand-made differences.
@@ -29,9 +30,23 @@ _DECL = re.compile(
     re.M)
 
 
-def annotate_text(text: str) -> tuple[str, int]:
-    """Returns the annotated text and the number of functions that were prefixed."""
+def _also_pattern(names):
+    alternatives = "|".join(re.escape(n) for n in names)
+    return re.compile(
+        r"^(?P<indent>[ \t]*)(?P<head>(?!return\b|else\b|STST_HD\b)[A-Za-z_:][^;{}()\n]*?[\s&*>])"
+        r"(?P<name>" + alternatives + r")\s*\((?P<args>[^;{}]*?)\)\s*(?:const\s*)?\{", re.M)
+
+
+def annotate_text(text: str, also=()) -> tuple[str, int]:
+    """Returns the annotated text and the number of functions that were prefixed. `also`: names of
+    further functions (defined in the text) that device code calls, e.g. a cell's `halo()` factory."""
     count = 0
+    if also:
+        def also_repl(m: re.Match) -> str:
+            nonlocal count
+            count += 1
+            return f"{m.group('indent')}STST_HD {m.group(0)[len(m.group('indent')):]}"
+        text = _also_pattern(also).sub(also_repl, text)
 
     def repl(m: re.Match) -> str:
         nonlocal count
@@ -41,8 +56,8 @@ def annotate_text(text: str) -> tuple[str, int]:
     return _DECL.sub(repl, text), count
 
 
-def annotate_file(src: Path, dst: Path) -> int:
-    text, count = annotate_text(src.read_text())
+def annotate_file(src: Path, dst: Path, also=()) -> int:
+    text, count = annotate_text(src.read_text(), also)
     dst.parent.mkdir(parents=True, exist_ok=True)
     dst.write_text(text)
     return count
@@ -52,9 +67,11 @@ def main() -> None:
     ap = argparse.ArgumentParser(description=__doc__.split("\n")[0])
     ap.add_argument("sources", nargs="+", type=Path)
     ap.add_argument("-o", "--out-dir", type=Path, required=True)
+    ap.add_argument("--also", default="", help="comma-separated names of further functions to annotate")
     args = ap.parse_args()
+    also = tuple(n for n in args.also.split(",") if n)
     for src in args.sources:
-        n = annotate_file(src, args.out_dir / src.name)
+        n = annotate_file(src, args.out_dir / src.name, also)
         print(f"{src} -> {args.out_dir / src.name}: {n} function(s) annotated")
 
 

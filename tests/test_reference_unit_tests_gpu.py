@@ -1,0 +1,26 @@
+"""The reference's own `unit_test_cuda` sources (tests/Stencil.cpp, tests/cuda/Grid.cpp,
+tests/cuda/StencilUpdate.cpp with GridTest.hpp / StencilUpdateTest.hpp / TransFuncs.hpp), built
+unmodified against this backend by stencilstream_b200/tools/build_reference_tests.py, must pass on the
+B200. The binary is produced in the build container (where /root/reference exists) and travels with
+the repository snapshot."""
+import subprocess
+from pathlib import Path
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+BINARY = Path(__file__).resolve().parent.parent / "build" / "ref_tests" / "unit_test_cuda_b200"
+
+
+def test_reference_cuda_unit_tests_pass():
+    if not BINARY.exists():
+        pytest.skip(f"{BINARY} not built (needs the reference tree at build time)")
+    proc = subprocess.run([str(BINARY)], capture_output=True, text=True, timeout=600)
+    print(proc.stdout)
+    assert proc.returncode == 0, proc.stdout + proc.stderr
+    lines = proc.stdout.splitlines()
+    passed = [line for line in lines if line.startswith("[ OK ]")]
+    # Stencil: 3, cuda::Grid: 4, cuda::StencilUpdate: 2 (normal + split cell structure)
+    assert len(passed) >= 8, proc.stdout
+    assert any("cuda::StencilUpdate (Split cell structure)" in line for line in passed)
+    assert any("cuda::Grid::copy_to_buffer" in line for line in passed)
