@@ -67,7 +67,8 @@ int stst_free(int device, void *ptr, stst_stream_t stream);
 int stst_malloc_ipc(int device, size_t bytes, void **ptr);
 int stst_free_ipc(int device, void *ptr);
 /* Pinned, portable host memory. Freed blocks are cached by size (STST_PINNED_CACHE_MB, default
- * 16384) because pinning gigabytes costs hundreds of milliseconds; stst_host_cache_trim releases them. */
+ * 16384) because pinning gigabytes costs hundreds of milliseconds; stst_host_cache_trim releases them.
+ * Requests above STST_PIN_LIMIT_MB (if set) fail, like requests the box cannot pin. */
 int stst_malloc_host(size_t bytes, void **ptr);
 int stst_free_host(void *ptr);
 int stst_host_cache_trim(void);
@@ -84,6 +85,21 @@ int stst_memcpy_2d_async(void *dst, size_t dst_pitch, const void *src, size_t sr
                          size_t width_bytes, size_t height, int kind, stst_stream_t stream);
 int stst_memcpy_peer_async(void *dst, int dst_device, const void *src, int src_device,
                            size_t bytes, stst_stream_t stream);
+/*
+ * Host memory that is not pinned (ordinary malloc / numpy / std::vector memory, or a grid image the
+ * box refused to pin): `rows` rows of `row_bytes` between host rows `host_pitch` apart and device
+ * rows `dev_pitch` apart, staged through a ring of three pinned slots (STST_STAGING_SLOT_MB, default
+ * 16) with the host-side copies spread over worker threads (STST_COPY_THREADS, default min(8,
+ * cores/2)) and overlapped with the DMA. kind: 0 = h2d, 1 = d2h. h2d returns once `host` may be
+ * reused (the last DMAs may still be in flight on `stream`); d2h returns when `host` holds the data.
+ * stst_memcpy_2d_auto picks the direct asynchronous copy when `host` is pinned, else the staged one.
+ */
+int stst_memcpy_2d_staged(void *dev, size_t dev_pitch, void *host, size_t host_pitch,
+                          size_t row_bytes, size_t rows, int kind, int device, stst_stream_t stream);
+int stst_memcpy_2d_auto(void *dev, size_t dev_pitch, void *host, size_t host_pitch, size_t row_bytes,
+                        size_t rows, int kind, int device, stst_stream_t stream);
+int stst_host_memcpy(void *dst, const void *src, size_t bytes); /* multi-threaded memcpy */
+int stst_host_is_pinned(const void *ptr, int *pinned);
 
 /* --- streams and events -------------------------------------------------------------------- */
 /* The per-device stream every StencilStream-B200 object uses unless told otherwise. */

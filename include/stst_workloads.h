@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define STST_WORKLOADS_ABI_VERSION 1
+#define STST_WORKLOADS_ABI_VERSION 2
 
 #define STST_OK 0
 #define STST_ERR_UNKNOWN_WORKLOAD (-1)
@@ -166,6 +166,29 @@ int stst_grid_sync_to_device(stst_grid *grid);
  * so the next update uploads the image first.
  */
 int stst_grid_host_accessor(stst_grid *grid, int mode, void **cells);
+/* Whether that host image exists and is pinned (boxes cap pinnable memory; a pageable image is moved
+ * through the runtime's staged pipeline, stst_memcpy_2d_staged in stst_rt.h). */
+int stst_grid_host_image_is_pinned(stst_grid *grid, int *pinned);
+
+/* ---- per-field operations (B200 extensions) ----------------------------------------------------
+ *
+ * The reference's applications compute max-norms and dump single fields on the host, through a
+ * GridAccessor that first migrates the whole array-of-structs grid (examples/convection/
+ * convection.cpp:412-438 and :460-477, examples/fdtd/src/fdtd.cpp:114-166). Grids are stored one
+ * plane per field here, so both run on the planes involved only.
+ * `field` is the index into the cell struct's members in declaration order (0 for scalar cells). */
+
+typedef struct stst_field_extent {
+    size_t field;
+    size_t rows, cols; /* the first `rows` rows and `cols` columns of the grid */
+} stst_field_extent;
+
+/* out[q] = max |cell.field_q| over extents[q] (-inf for an empty extent); one device pass for up to
+ * 8 extents. Comparison as in the reference loop: `abs(v) > max`, i.e. NaNs are never selected. */
+int stst_grid_max_abs(stst_grid *grid, const stst_field_extent *extents, size_t n, double *out);
+/* Dense rows x cols array of ONE field; bytes must equal rows*cols*sizeof(field), else STST_ERR_RANGE. */
+int stst_grid_copy_field_to_host(stst_grid *grid, size_t field, void *values, size_t bytes);
+int stst_grid_copy_field_from_host(stst_grid *grid, size_t field, const void *values, size_t bytes);
 
 /* ---- updaters ------------------------------------------------------------------------------------ */
 
@@ -255,6 +278,12 @@ int stst_slab_copy_rows_from_host(stst_slab *slab, size_t first_row, size_t n_ro
 int stst_slab_copy_rows_to_host(stst_slab *slab, size_t first_row, size_t n_rows, void *cells,
                                 size_t bytes);
 int stst_slab_exchange_halos(stst_slab *slab);
+/* As stst_grid_max_abs, extents in GLOBAL grid coordinates; out[q] covers the rows this slab owns
+ * (-inf if none): combine the slabs' results with max (across processes: an all-reduce). */
+int stst_slab_max_abs(stst_slab *slab, const stst_field_extent *extents, size_t n, double *out);
+/* ONE field of `n_rows` owned rows from slab-local row `first_row` on. */
+int stst_slab_copy_field_rows_to_host(stst_slab *slab, size_t field, size_t first_row, size_t n_rows,
+                                      void *values, size_t bytes);
 /* Uses transition_function, halo_value, iteration_offset, n_iterations and blocking of `params`. */
 int stst_slab_update(stst_slab *slab, const stst_update_params *params);
 int stst_slab_synchronize(stst_slab *slab);

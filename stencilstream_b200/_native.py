@@ -92,6 +92,10 @@ class UpdateStats(C.Structure):
     ]
 
 
+class FieldExtent(C.Structure):
+    _fields_ = [("field", C.c_size_t), ("rows", C.c_size_t), ("cols", C.c_size_t)]
+
+
 class DeviceInfo(C.Structure):
     _fields_ = [
         ("sm_count", C.c_int), ("cc_major", C.c_int), ("cc_minor", C.c_int),
@@ -118,6 +122,33 @@ CELL_DTYPES = {
 CELL_DTYPES["convection_thermal"] = CELL_DTYPES["convection_pt"]
 CELL_DTYPES["kat_r2"] = CELL_DTYPES["kat"]
 
+
+
+def field_index(workload: str, field) -> int:
+    """Plane index of `field` (a member name of the workload's cell struct, or already an index)."""
+    if isinstance(field, (int, np.integer)):
+        return int(field)
+    names = CELL_DTYPES[workload].names
+    if not names or field not in names:
+        raise KeyError(f"workload {workload!r} has no cell field {field!r}")
+    return names.index(field)
+
+
+def field_dtype(workload: str, field) -> np.dtype:
+    dtype = CELL_DTYPES[workload]
+    if not dtype.names:
+        return dtype
+    return dtype[dtype.names[field_index(workload, field)]]
+
+
+def field_extents(workload: str, extents):
+    """ctypes array of FieldExtent from [(field, rows, cols), ...]."""
+    arr = (FieldExtent * max(len(extents), 1))()
+    for q, (field, rows, cols) in enumerate(extents):
+        arr[q].field, arr[q].rows, arr[q].cols = field_index(workload, field), int(rows), int(cols)
+    return arr
+
+
 PARAM_TYPES = {
     "conway": ConwayParams,
     "jacobi5": Jacobi5Params,
@@ -138,7 +169,8 @@ RT_SYMBOLS = [
     "stst_set_device", "stst_malloc", "stst_free", "stst_malloc_ipc", "stst_free_ipc",
     "stst_malloc_host", "stst_free_host", "stst_host_cache_trim", "stst_host_register", "stst_host_unregister",
     "stst_memset_async", "stst_memcpy_h2d_async", "stst_memcpy_d2h_async", "stst_memcpy_d2d_async",
-    "stst_memcpy_2d_async", "stst_memcpy_peer_async", "stst_default_stream", "stst_stream_create",
+    "stst_memcpy_2d_async", "stst_memcpy_peer_async",
+    "stst_memcpy_2d_staged", "stst_memcpy_2d_auto", "stst_host_memcpy", "stst_host_is_pinned", "stst_default_stream", "stst_stream_create",
     "stst_stream_destroy", "stst_stream_synchronize", "stst_stream_wait_event", "stst_event_create",
     "stst_event_destroy", "stst_event_record", "stst_event_synchronize", "stst_event_elapsed_ms",
     "stst_device_synchronize", "stst_stream_write_value32", "stst_stream_wait_value32_geq", "stst_tensor_map_encode_2d", "stst_peer_can_access",
@@ -152,7 +184,9 @@ WORKLOADS_SYMBOLS = [
     "stst_workloads_abi_version", "stst_workloads_last_error", "stst_workload_count",
     "stst_workload_name", "stst_workload_get_info", "stst_grid_create", "stst_grid_share",
     "stst_grid_make_similar", "stst_grid_destroy", "stst_grid_shape", "stst_grid_copy_from_host",
-    "stst_grid_copy_to_host", "stst_grid_sync_to_device", "stst_grid_host_accessor", "stst_update_create",
+    "stst_grid_copy_to_host", "stst_grid_sync_to_device", "stst_grid_host_accessor", "stst_grid_host_image_is_pinned",
+    "stst_grid_max_abs", "stst_grid_copy_field_to_host", "stst_grid_copy_field_from_host",
+    "stst_slab_max_abs", "stst_slab_copy_field_rows_to_host", "stst_update_create",
     "stst_update_set_params", "stst_update_apply", "stst_update_get_stats", "stst_update_destroy",
     "stst_slab_create", "stst_slab_destroy", "stst_slab_get_info", "stst_slab_get_ipc_handle",
     "stst_slab_attach_ipc", "stst_slab_attach_local", "stst_slab_copy_from_host",
@@ -207,6 +241,15 @@ def workloads_lib(strict: bool | None = None):
         lib.stst_grid_copy_to_host.argtypes = [vp, vp, C.c_size_t]
         lib.stst_grid_sync_to_device.argtypes = [vp]
         lib.stst_grid_host_accessor.argtypes = [vp, C.c_int, C.POINTER(vp)]
+        lib.stst_grid_host_image_is_pinned.argtypes = [vp, C.POINTER(C.c_int)]
+        lib.stst_grid_max_abs.argtypes = [vp, C.POINTER(FieldExtent), C.c_size_t,
+                                          C.POINTER(C.c_double)]
+        lib.stst_grid_copy_field_to_host.argtypes = [vp, C.c_size_t, vp, C.c_size_t]
+        lib.stst_grid_copy_field_from_host.argtypes = [vp, C.c_size_t, vp, C.c_size_t]
+        lib.stst_slab_max_abs.argtypes = [vp, C.POINTER(FieldExtent), C.c_size_t,
+                                          C.POINTER(C.c_double)]
+        lib.stst_slab_copy_field_rows_to_host.argtypes = [vp, C.c_size_t, C.c_size_t, C.c_size_t, vp,
+                                                          C.c_size_t]
         lib.stst_update_create.argtypes = [C.c_char_p, C.POINTER(UpdateParams), C.POINTER(vp)]
         lib.stst_update_set_params.argtypes = [vp, C.POINTER(UpdateParams)]
         lib.stst_update_apply.argtypes = [vp, vp, C.POINTER(vp)]

@@ -160,6 +160,41 @@ class Grid:
         self.copy_to_buffer(out)
         return out
 
+    def host_image_is_pinned(self) -> bool:
+        """Whether the accessor's host image is pinned memory (else it is moved through the staged
+        pipeline of the runtime; boxes cap how much memory can be pinned)."""
+        pinned = C.c_int()
+        _check(self._lib, self._lib.stst_grid_host_image_is_pinned(self._handle, C.byref(pinned)))
+        return bool(pinned.value)
+
+    # -- B200 extensions: per-field device operations (include/stst_workloads.h) ----------------------
+    def max_abs(self, extents) -> list[float]:
+        """[(field, rows, cols), ...] -> max |cell.field| over the first rows x cols cells, evaluated
+        on the device in one pass (the host loop of reference examples/convection/convection.cpp:412-438
+        without migrating the grid). `field` is a member name of the cell struct or its index."""
+        extents = list(extents)
+        out = (C.c_double * max(len(extents), 1))()
+        _check(self._lib, self._lib.stst_grid_max_abs(
+            self._handle, _native.field_extents(self.workload, extents), len(extents), out))
+        return [float(out[q]) for q in range(len(extents))]
+
+    def field_to_numpy(self, field) -> np.ndarray:
+        """ONE field of every cell as a dense 2-D array (single-plane download)."""
+        out = np.empty(self.get_grid_range(), dtype=_native.field_dtype(self.workload, field))
+        _check(self._lib, self._lib.stst_grid_copy_field_to_host(
+            self._handle, _native.field_index(self.workload, field),
+            out.ctypes.data_as(C.c_void_p), out.nbytes))
+        return out
+
+    def copy_field_from_buffer(self, field, values) -> None:
+        """Overwrite ONE field of every cell; `values` must have the grid's extent (else RangeError)."""
+        arr = np.ascontiguousarray(values, dtype=_native.field_dtype(self.workload, field))
+        if arr.ndim != 2 or tuple(arr.shape) != self.get_grid_range():
+            raise RangeError("The target buffer has not the same size as the grid")
+        _check(self._lib, self._lib.stst_grid_copy_field_from_host(
+            self._handle, _native.field_index(self.workload, field),
+            arr.ctypes.data_as(C.c_void_p), arr.nbytes))
+
     def share(self) -> "Grid":
         handle = C.c_void_p()
         _check(self._lib, self._lib.stst_grid_share(self._handle, C.byref(handle)))

@@ -1,0 +1,122 @@
+"""Application loops around the generation loop — the callers on either side of the hot path.
+
+Host-side mirrors of the two reference applications that do more than one `StencilUpdate` call:
+
+* `run_convection`  — reference examples/convection/convection.cpp:402-477: batches of `nerr`
+  pseudo-transient iterations until the velocity/pressure residuals fall below `epsilon`, then one
+  thermal-solver iteration whose time step depends on the velocity maxima; repeated `nt` times.
+* `run_fdtd`        — reference examples/fdtd/src/fdtd.cpp:218-252: the simulation in snapshot
+  intervals with a live `iteration_offset`, one `hz` frame per interval, `hz_sum` at the end.
+
+What differs from the reference is where the glue runs. There the five max-norms of a convergence
+check are a host loop over a `GridAccessor`, which first migrates the whole 88-byte-per-cell grid
+over PCIe (convection.cpp:412-438), and frames are written from a full-grid accessor
+(fdtd.cpp:114-166, convection.cpp:460-477). Here norms are one device pass over the five planes
+involved (`Grid.max_abs`, kernel `reduce_max_abs_kernel`) and a frame is a single-plane download
+(`Grid.field_to_numpy`); the cells never leave HBM between updates. Every number is computed by
+libstst_workloads.so; this module only sequences calls, as the reference's `main` functions do.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Callable
+
+import numpy as np
+
+from .api import Grid, Params, StencilUpdate
+from . import workloads as W
+
+
+@dataclass
+class ConvectionStep:
+    """What the reference prints per time step (convection.cpp:447-448) plus the chosen dt."""
+    it: int
+    iterations: int
+    errV: float
+    errP: float
+    dt: float
+    norms: dict = field(default_factory=dict)
+
+
+def convection_norm_extents(nx: int, ny: int):
+    """(field, rows, cols) of the five max-norms, index ranges as in convection.cpp:417-434 (the
+    grid is (nx+1) x (ny+1) cells, x the row index)."""
+    return [("ErrV", nx, ny + 1), ("ErrP", nx, ny), ("Vx", nx + 1, ny), ("Vy", nx, ny),
+            ("Pt", nx, ny)]
+
+
+def run_convection(config: dict, *, cells: np.ndarray | None = None, strict: bool | None = None,
+                   device: int = -1, fused_iterations: int = 0,
+                   on_frame: Callable[[int, np.ndarray], None] | None = None):
+    """Run a whole convection experiment (`config`: the reference's experiment JSON as a dict).
+
+    Returns (final Grid, [ConvectionStep, ...]). `on_frame(it, T)` receives the temperature field of
+    the inner nx x ny cells every `nout` steps (what the reference writes to `<it>.csv`).
+    """
+    exp = W.ConvectionExperiment(config)
+    nx, ny = exp.nx, exp.ny
+    iter_max, nt = int(config["iterMax"]), int(config["nt"])
+    nout, nerr, epsilon = int(config["nout"]), int(config["nerr"]), float(config["epsilon"])
+    if cells is None:
+        cells = exp.initial_grid()
+    grid = Grid("convection_pt", buffer=cells, device=device, strict=strict)
+    pseudo_transient = StencilUpdate(
+        "convection_pt", Params(transition_function=exp.pseudo_transient_params(), halo_value=None,
+                                n_iterations=nerr, blocking=True,
+                                fused_iterations=fused_iterations), strict=strict)
+    extents = convection_norm_extents(nx, ny)
+    steps = []
+    for it in range(1, nt + 1):
+        errV = errP = 2 * epsilon
+        norms = dict.fromkeys((e[0] for e in extents), float("-inf"))
+        iterations = 0
+        while iterations < iter_max and (errV > epsilon or errP > epsilon):
+            grid = pseudo_transient(grid)
+            norms = dict(zip((e[0] for e in extents), grid.max_abs(extents)))
+            errV = norms["ErrV"] / (1e-12 + norms["Vy"])
+            errP = norms["ErrP"] / (1e-12 + norms["Pt"])
+            iterations += nerr
+        with np.errstate(divide="ignore"):
+            dt_adv = min(np.float64(exp.dx) / norms["Vx"], np.float64(exp.dy) / norms["Vy"]) / 2.1
+        dt = float(min(exp.dt_diff, dt_adv))
+        thermal = StencilUpdate(
+            "convection_thermal", Params(transition_function=exp.thermal_params(dt), halo_value=None,
+                                         n_iterations=1, blocking=True), strict=strict)
+        grid = thermal(grid)
+        steps.append(ConvectionStep(it, iterations, errV, errP, dt, norms))
+        if on_frame is not None and it % nout == 0:
+            on_frame(it, grid.field_to_numpy("T")[:nx, :ny])
+    return grid, steps
+
+
+def run_fdtd(config: dict, *, n_timesteps: int | None = None, n_snap_timesteps: int | None = None,
+             cells: np.ndarray | None = None, strict: bool | None = None, device: int = -1,
+             fused_iterations: int = 0,
+             on_frame: Callable[[str, int, np.ndarray], None] | None = None):
+    """Run an FDTD experiment (`config`: the reference's experiment JSON as a dict) in snapshot
+    intervals. `on_frame(field, iteration, values)` receives the `hz` plane after every interval and
+    `hz_sum` at the end (fdtd.cpp:233-250). `n_timesteps` / `n_snap_timesteps` override the
+    experiment's values (tests shorten the run). Returns (final Grid, StencilUpdate)."""
+    exp = W.FdtdExperiment(config)
+    total = exp.n_timesteps() if n_timesteps is None else int(n_timesteps)
+    snap = exp.n_snap_timesteps() if n_snap_timesteps is None else int(n_snap_timesteps)
+    if cells is None:
+        cells = exp.initial_grid()
+    grid = Grid("fdtd", buffer=cells, device=device, strict=strict)
+    simulation = StencilUpdate(
+        "fdtd", Params(transition_function=exp.kernel_params(), halo_value=None, iteration_offset=0,
+                       n_iterations=total, blocking=True, fused_iterations=fused_iterations),
+        strict=strict)
+    if snap:
+        params = simulation.get_params()
+        params.n_iterations = snap
+        while params.iteration_offset < total:
+            grid = simulation(grid)
+            if on_frame is not None:
+                on_frame("hz", params.iteration_offset + snap, grid.field_to_numpy("hz"))
+            params.iteration_offset += snap
+    else:
+        grid = simulation(grid)
+    if on_frame is not None:
+        on_frame("hz_sum", total, grid.field_to_numpy("hz_sum"))
+    return grid, simulation

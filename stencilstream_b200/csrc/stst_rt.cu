@@ -12,11 +12,16 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 
+#include <algorithm>
+#include <atomic>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <mutex>
+#include <thread>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -251,6 +256,12 @@ int stst_malloc_host(size_t bytes, void **ptr) {
         return fail(-1, "stst_malloc_host", "null argument");
     if (bytes == 0)
         bytes = 64;
+    // STST_PIN_LIMIT_MB: refuse larger requests (callers then use pageable memory and the staged
+    // transfer pipeline) — for boxes with little pinnable memory, and to test that path.
+    if (const char *env = std::getenv("STST_PIN_LIMIT_MB")) {
+        if (*env && bytes > (size_t(std::strtoull(env, nullptr, 10)) << 20))
+            return fail(-1, "stst_malloc_host", "request exceeds STST_PIN_LIMIT_MB");
+    }
     {
         std::lock_guard<std::mutex> lock(g_pinned_mutex);
         auto it = g_pinned_free.find(bytes);
@@ -345,6 +356,244 @@ int stst_memcpy_2d_async(void *dst, size_t dst_pitch, const void *src, size_t sr
     STST_CUDA(cudaMemcpy2DAsync(dst, dst_pitch, src, src_pitch, width_bytes, height, k,
                                 as_stream(stream)));
     return 0;
+}
+
+// ---- staged copies: pageable host memory <-> device through a small pinned ring -------------------
+//
+// Pinning a whole grid image is the fastest host side for a transfer, but it is not always possible:
+// boxes cap pinnable memory (the round-1 B200 pool: cudaHostAlloc starts failing around 4 GiB although
+// RLIMIT_MEMLOCK is unlimited), callers hand in ordinary numpy / std::vector memory, and pinning costs
+// ~0.4 s per GiB the first time. A plain cudaMemcpy from pageable memory runs at a fraction of the
+// link rate because the driver stages it through one small buffer with a single copying thread. The
+// pipeline below does that staging itself: a ring of pinned slots, host-side copies spread over a
+// few worker threads, the DMA of slot i overlapping the host copy of slot i+1.
+namespace {
+
+class CopyWorkers {
+  public:
+    static CopyWorkers &instance() {
+        static CopyWorkers *pool = new CopyWorkers(); // leaked on purpose: no shutdown-order issues
+        return *pool;
+    }
+
+    /// dst[0, bytes) = src[0, bytes), split over the workers (the caller copies a share as well).
+    void copy(void *dst, const void *src, size_t bytes) {
+        std::lock_guard<std::mutex> one_job(call_mutex);
+        const size_t n = threads.size() + 1;
+        if (bytes < (size_t(4) << 20) || n == 1) {
+            std::memcpy(dst, src, bytes);
+            return;
+        }
+        const size_t slice = ((bytes + n - 1) / n + 4095) / 4096 * 4096;
+        {
+            std::lock_guard<std::mutex> lock(mutex);
+            job_dst = static_cast<unsigned char *>(dst);
+            job_src = static_cast<const unsigned char *>(src);
+            job_bytes = bytes;
+            job_slice = slice;
+            pending = threads.size();
+            generation++;
+        }
+        wake.notify_all();
+        run_slice(0);
+        std::unique_lock<std::mutex> lock(mutex);
+        done.wait(lock, [&] { return pending == 0; });
+    }
+
+  private:
+    CopyWorkers() {
+        unsigned n = std::max(1u, std::min(8u, std::thread::hardware_concurrency() / 2));
+        if (const char *env = std::getenv("STST_COPY_THREADS"))
+            n = std::max(1, std::atoi(env));
+        for (unsigned i = 1; i < n; i++)
+            threads.emplace_back([this, i] { loop(i); }).detach();
+    }
+
+    void run_slice(size_t index) {
+        const size_t lo = index * job_slice;
+        if (lo < job_bytes)
+            std::memcpy(job_dst + lo, job_src + lo, std::min(job_slice, job_bytes - lo));
+    }
+
+    void loop(size_t index) {
+        unsigned long long seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lock(mutex);
+                wake.wait(lock, [&] { return generation != seen; });
+                seen = generation;
+            }
+            run_slice(index);
+            {
+                std::lock_guard<std::mutex> lock(mutex);
+                pending--;
+            }
+            done.notify_one();
+        }
+    }
+
+    std::vector<std::thread> threads;
+    std::mutex call_mutex, mutex;
+    std::condition_variable wake, done;
+    unsigned char *job_dst = nullptr;
+    const unsigned char *job_src = nullptr;
+    size_t job_bytes = 0, job_slice = 0, pending = 0;
+    unsigned long long generation = 0;
+};
+
+struct StagingRing {
+    static constexpr int slots = 3;
+    size_t slot_bytes = 0;
+    void *slot[slots] = {};
+    cudaEvent_t idle[slots] = {}; // recorded behind the last DMA that touched the slot
+    bool used[slots] = {};
+};
+
+std::mutex g_staging_mutex;
+std::map<int, StagingRing> g_staging; // per device (events belong to a device)
+
+size_t staging_slot_bytes() {
+    static const size_t bytes = [] {
+        const char *env = std::getenv("STST_STAGING_SLOT_MB");
+        const size_t mb = (env && *env) ? size_t(std::strtoull(env, nullptr, 10)) : size_t(16);
+        return std::max<size_t>(mb, 1) << 20;
+    }();
+    return bytes;
+}
+
+bool host_pointer_is_pinned(const void *ptr) {
+    cudaPointerAttributes attr{};
+    if (cudaPointerGetAttributes(&attr, ptr) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return false;
+    }
+    return attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged;
+}
+
+} // namespace
+
+int stst_host_memcpy(void *dst, const void *src, size_t bytes) {
+    if (bytes != 0 && (!dst || !src))
+        return fail(-1, "stst_host_memcpy", "null argument");
+    CopyWorkers::instance().copy(dst, src, bytes);
+    return 0;
+}
+
+int stst_host_is_pinned(const void *ptr, int *pinned) {
+    if (!pinned)
+        return fail(-1, "stst_host_is_pinned", "null argument");
+    *pinned = host_pointer_is_pinned(ptr) ? 1 : 0;
+    return 0;
+}
+
+int stst_memcpy_2d_staged(void *dev, size_t dev_pitch, void *host, size_t host_pitch,
+                          size_t row_bytes, size_t rows, int kind, int device,
+                          stst_stream_t stream) {
+    if (row_bytes == 0 || rows == 0)
+        return 0;
+    if (kind != 0 && kind != 1)
+        return fail(-1, "stst_memcpy_2d_staged", "kind must be 0 (h2d) or 1 (d2h)");
+    const bool h2d = kind == 0;
+    const size_t slot_bytes = std::max(staging_slot_bytes(), row_bytes);
+    std::lock_guard<std::mutex> lock(g_staging_mutex);
+    DeviceGuard guard;
+    STST_CUDA(guard.enter(device));
+    StagingRing &ring = g_staging[device];
+    if (ring.slot_bytes < slot_bytes) {
+        for (int i = 0; i < StagingRing::slots; i++) {
+            if (ring.slot[i]) {
+                if (ring.used[i])
+                    STST_CUDA(cudaEventSynchronize(ring.idle[i]));
+                STST_CUDA(cudaFreeHost(ring.slot[i]));
+                ring.slot[i] = nullptr;
+            }
+            if (!ring.idle[i])
+                STST_CUDA(cudaEventCreateWithFlags(&ring.idle[i], cudaEventDisableTiming));
+            STST_CUDA(cudaHostAlloc(&ring.slot[i], slot_bytes, cudaHostAllocPortable));
+            ring.used[i] = false;
+        }
+        ring.slot_bytes = slot_bytes;
+    }
+    const size_t chunk_rows = std::max<size_t>(1, ring.slot_bytes / row_bytes);
+    const size_t n_chunks = (rows + chunk_rows - 1) / chunk_rows;
+    unsigned char *hp = static_cast<unsigned char *>(host);
+    unsigned char *dp = static_cast<unsigned char *>(dev);
+    CopyWorkers &workers = CopyWorkers::instance();
+    cudaStream_t cs = as_stream(stream);
+
+    // host rows <-> densely packed rows in a slot
+    auto host_copy = [&](int s, size_t row0, size_t n, bool into_slot) {
+        unsigned char *slot = static_cast<unsigned char *>(ring.slot[s]);
+        unsigned char *h = hp + row0 * host_pitch;
+        if (host_pitch == row_bytes) {
+            if (into_slot)
+                workers.copy(slot, h, n * row_bytes);
+            else
+                workers.copy(h, slot, n * row_bytes);
+        } else {
+            for (size_t r = 0; r < n; r++) {
+                if (into_slot)
+                    std::memcpy(slot + r * row_bytes, h + r * host_pitch, row_bytes);
+                else
+                    std::memcpy(h + r * host_pitch, slot + r * row_bytes, row_bytes);
+            }
+        }
+    };
+
+    if (h2d) {
+        for (size_t c = 0; c < n_chunks; c++) {
+            const int s = int(c % StagingRing::slots);
+            const size_t row0 = c * chunk_rows, n = std::min(chunk_rows, rows - row0);
+            if (ring.used[s])
+                STST_CUDA(cudaEventSynchronize(ring.idle[s]));
+            host_copy(s, row0, n, true);
+            STST_CUDA(cudaMemcpy2DAsync(dp + row0 * dev_pitch, dev_pitch, ring.slot[s], row_bytes,
+                                        row_bytes, n, cudaMemcpyHostToDevice, cs));
+            STST_CUDA(cudaEventRecord(ring.idle[s], cs));
+            ring.used[s] = true;
+        }
+        return 0;
+    }
+    auto drain = [&](size_t c) -> int {
+        const int s = int(c % StagingRing::slots);
+        const size_t row0 = c * chunk_rows, n = std::min(chunk_rows, rows - row0);
+        STST_CUDA(cudaEventSynchronize(ring.idle[s]));
+        host_copy(s, row0, n, false);
+        return 0;
+    };
+    for (size_t c = 0; c < n_chunks; c++) {
+        const int s = int(c % StagingRing::slots);
+        const size_t row0 = c * chunk_rows, n = std::min(chunk_rows, rows - row0);
+        if (c >= size_t(StagingRing::slots)) {
+            if (int st = drain(c - StagingRing::slots))
+                return st;
+        } else if (ring.used[s]) {
+            STST_CUDA(cudaEventSynchronize(ring.idle[s]));
+        }
+        STST_CUDA(cudaMemcpy2DAsync(ring.slot[s], row_bytes, dp + row0 * dev_pitch, dev_pitch,
+                                    row_bytes, n, cudaMemcpyDeviceToHost, cs));
+        STST_CUDA(cudaEventRecord(ring.idle[s], cs));
+        ring.used[s] = true;
+    }
+    for (size_t c = n_chunks > size_t(StagingRing::slots) ? n_chunks - StagingRing::slots : 0;
+         c < n_chunks; c++) {
+        if (int st = drain(c))
+            return st;
+    }
+    return 0;
+}
+
+int stst_memcpy_2d_auto(void *dev, size_t dev_pitch, void *host, size_t host_pitch,
+                        size_t row_bytes, size_t rows, int kind, int device, stst_stream_t stream) {
+    if (row_bytes == 0 || rows == 0)
+        return 0;
+    if (host_pointer_is_pinned(host)) {
+        if (kind == 0)
+            return stst_memcpy_2d_async(dev, dev_pitch, host, host_pitch, row_bytes, rows, 0, stream);
+        return stst_memcpy_2d_async(host, host_pitch, dev, dev_pitch, row_bytes, rows, 1, stream);
+    }
+    return stst_memcpy_2d_staged(dev, dev_pitch, host, host_pitch, row_bytes, rows, kind, device,
+                                 stream);
 }
 
 int stst_memcpy_peer_async(void *dst, int dst_device, const void *src, int src_device,

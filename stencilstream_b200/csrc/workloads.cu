@@ -12,6 +12,7 @@
 
 #include "workloads/functors.hpp"
 
+#include <algorithm>
 #include <cstring>
 #include <memory>
 #include <stdexcept>
@@ -42,6 +43,10 @@ struct GridBase {
     virtual void copy_to_host(void *cells) = 0;
     virtual void sync_to_device() = 0;
     virtual void *host_accessor(int mode) = 0;
+    virtual bool host_pinned() = 0;
+    virtual void max_abs(const stst_field_extent *extents, std::size_t n, double *out) = 0;
+    virtual std::size_t field_bytes(std::size_t field) const = 0;
+    virtual void copy_field(std::size_t field, void *host, bool to_device) = 0;
     virtual GridBase *share() = 0;
     virtual GridBase *make_similar() = 0;
 };
@@ -53,13 +58,11 @@ template <typename Cell> struct GridHolder final : GridBase {
     std::size_t cols() const override { return grid.get_grid_width(); }
     std::size_t cell_bytes() const override { return sizeof(Cell); }
     void copy_from_host(const void *cells) override {
-        // copy_from_buffer semantics without the intermediate sycl::buffer: fill the host image.
-        typename sc::Grid<Cell>::template GridAccessor<sycl::access::mode::write> ac(grid);
-        std::memcpy(static_cast<void *>(ac.get_pointer()), cells, ac.byte_size());
+        // copy_from_buffer semantics without the intermediate sycl::buffer
+        grid.copy_from_host(static_cast<const Cell *>(cells));
     }
     void copy_to_host(void *cells) override {
-        typename sc::Grid<Cell>::template GridAccessor<sycl::access::mode::read> ac(grid);
-        std::memcpy(cells, static_cast<const void *>(ac.get_pointer()), ac.byte_size());
+        grid.copy_to_host(static_cast<Cell *>(cells));
     }
     void sync_to_device() override {
         grid.get_storage().require_device();
@@ -72,6 +75,23 @@ template <typename Cell> struct GridHolder final : GridBase {
         }
         typename sc::Grid<Cell>::template GridAccessor<sycl::access::mode::read_write> ac(grid);
         return static_cast<void *>(ac.get_pointer());
+    }
+    bool host_pinned() override { return grid.get_storage().host_mirror_is_pinned(); }
+    void max_abs(const stst_field_extent *extents, std::size_t n, double *out) override {
+        std::vector<sc::FieldExtent> list(n);
+        for (std::size_t q = 0; q < n; q++)
+            list[q] = sc::FieldExtent{extents[q].field, extents[q].rows, extents[q].cols};
+        const std::vector<double> result = grid.max_abs(list);
+        std::copy(result.begin(), result.end(), out);
+    }
+    std::size_t field_bytes(std::size_t field) const override {
+        return sc::Grid<Cell>::plane_element_bytes(field);
+    }
+    void copy_field(std::size_t field, void *host, bool to_device) override {
+        if (to_device)
+            grid.copy_plane_from_host(field, host);
+        else
+            grid.copy_plane_to_host(field, host);
     }
     GridBase *share() override { return new GridHolder(workload, grid); }
     GridBase *make_similar() override { return new GridHolder(workload, grid.make_similar()); }
@@ -154,6 +174,10 @@ struct SlabBase {
     virtual void upload(const void *cells, std::size_t first_row, std::size_t n_rows) = 0;
     virtual void download(void *cells, std::size_t first_row, std::size_t n_rows) = 0;
     virtual void exchange() = 0;
+    virtual void max_abs(const stst_field_extent *extents, std::size_t n, double *out) = 0;
+    virtual std::size_t field_bytes(std::size_t field) const = 0;
+    virtual void download_field(std::size_t field, void *host, std::size_t first_row,
+                                std::size_t n_rows) = 0;
     virtual void update(const stst_update_params &p) = 0;
     virtual void synchronize() = 0;
     virtual void record(void *event) = 0;
@@ -209,6 +233,22 @@ template <typename F, typename ParamBlock> struct SlabHolder final : SlabBase {
         slab->download_rows(static_cast<Cell *>(cells), first_row, n_rows);
     }
     void exchange() override { slab->exchange_halos(); }
+    void max_abs(const stst_field_extent *extents, std::size_t n, double *out) override {
+        std::vector<std::size_t> planes(n), rows(n), cols(n);
+        for (std::size_t q = 0; q < n; q++) {
+            planes[q] = extents[q].field;
+            rows[q] = extents[q].rows;
+            cols[q] = extents[q].cols;
+        }
+        slab->max_abs(n, planes.data(), rows.data(), cols.data(), out);
+    }
+    std::size_t field_bytes(std::size_t field) const override {
+        return sc::Grid<Cell>::plane_element_bytes(field);
+    }
+    void download_field(std::size_t field, void *host, std::size_t first_row,
+                        std::size_t n_rows) override {
+        slab->download_plane_rows(field, host, first_row, n_rows);
+    }
     void update(const stst_update_params &p) override {
         auto params = UpdateHolder<F, ParamBlock>::convert(p);
         slab->run(params.transition_function, params.halo_value, params.iteration_offset,
@@ -421,6 +461,47 @@ STST_EXPORT int stst_grid_host_accessor(stst_grid *grid, int mode, void **cells)
     });
 }
 
+STST_EXPORT int stst_grid_host_image_is_pinned(stst_grid *grid, int *pinned) {
+    if (!grid || !pinned)
+        return report(STST_ERR_INVALID_ARGUMENT, "null argument");
+    *pinned = grid->impl->host_pinned() ? 1 : 0;
+    return STST_OK;
+}
+
+STST_EXPORT int stst_grid_max_abs(stst_grid *grid, const stst_field_extent *extents, size_t n,
+                                  double *out) {
+    if (!grid || (n != 0 && (!extents || !out)))
+        return report(STST_ERR_INVALID_ARGUMENT, "null argument");
+    return guarded([&] {
+        grid->impl->max_abs(extents, n, out);
+        return STST_OK;
+    });
+}
+
+namespace {
+int grid_copy_field(stst_grid *grid, size_t field, void *host, size_t bytes, bool to_device) {
+    if (!grid || (!host && bytes != 0))
+        return report(STST_ERR_INVALID_ARGUMENT, "null argument");
+    return guarded([&] {
+        const size_t want = grid->impl->rows() * grid->impl->cols() * grid->impl->field_bytes(field);
+        if (bytes != want)
+            return report(STST_ERR_RANGE, "The target buffer has not the same size as the field");
+        grid->impl->copy_field(field, host, to_device);
+        return STST_OK;
+    });
+}
+} // namespace
+
+STST_EXPORT int stst_grid_copy_field_to_host(stst_grid *grid, size_t field, void *values,
+                                             size_t bytes) {
+    return grid_copy_field(grid, field, values, bytes, false);
+}
+
+STST_EXPORT int stst_grid_copy_field_from_host(stst_grid *grid, size_t field, const void *values,
+                                               size_t bytes) {
+    return grid_copy_field(grid, field, const_cast<void *>(values), bytes, true);
+}
+
 STST_EXPORT int stst_update_create(const char *workload, const stst_update_params *params,
                                    stst_update **update) {
     const WorkloadEntry *e = find(workload);
@@ -596,6 +677,32 @@ STST_EXPORT int stst_slab_exchange_halos(stst_slab *slab) {
         return report(STST_ERR_INVALID_ARGUMENT, "null argument");
     return guarded([&] {
         slab->impl->exchange();
+        return STST_OK;
+    });
+}
+
+STST_EXPORT int stst_slab_max_abs(stst_slab *slab, const stst_field_extent *extents, size_t n,
+                                  double *out) {
+    if (!slab || (n != 0 && (!extents || !out)))
+        return report(STST_ERR_INVALID_ARGUMENT, "null argument");
+    return guarded([&] {
+        slab->impl->max_abs(extents, n, out);
+        return STST_OK;
+    });
+}
+
+STST_EXPORT int stst_slab_copy_field_rows_to_host(stst_slab *slab, size_t field, size_t first_row,
+                                                  size_t n_rows, void *values, size_t bytes) {
+    if (!slab || (!values && bytes != 0))
+        return report(STST_ERR_INVALID_ARGUMENT, "null argument");
+    return guarded([&] {
+        stst_slab_info info;
+        slab->impl->info(info);
+        const size_t owned = info.row_hi - info.row_lo;
+        if (first_row > owned || n_rows > owned - first_row ||
+            bytes != n_rows * info.grid_cols * slab->impl->field_bytes(field))
+            return report(STST_ERR_RANGE, "The target buffer has not the same size as the field rows");
+        slab->impl->download_field(field, values, first_row, n_rows);
         return STST_OK;
     });
 }

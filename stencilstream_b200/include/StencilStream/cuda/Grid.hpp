@@ -16,6 +16,7 @@
  * at the same points where SYCL would migrate: accessor construction and the next update.
  */
 #pragma once
+#include "internal/FieldOps.hpp"
 #include "internal/Helpers.hpp"
 #include "internal/Runtime.hpp"
 #include "internal/TileKernel.hpp"
@@ -27,9 +28,17 @@
 #include <cstring>
 #include <memory>
 #include <stdexcept>
+#include <vector>
 
 namespace stencil {
 namespace cuda {
+
+/// B200 extension: "field `plane` (index into `Cell::fields`; 0 for scalar cells), restricted to the
+/// first `rows` rows and `cols` columns of the grid" — the operand of `Grid::max_abs`.
+struct FieldExtent {
+    std::size_t plane;
+    std::size_t rows, cols;
+};
 
 namespace internal {
 
@@ -158,20 +167,36 @@ template <typename Cell> class GridStorage {
   private:
     static constexpr std::size_t staging_bytes = std::size_t(64) << 20;
 
-    std::size_t rows_per_chunk() const {
+    std::size_t rows_per_chunk(const void *host_ptr) const {
+        // Pageable host memory goes through the runtime's pinned staging ring, which drains at the
+        // end of every call: use larger device-side chunks there so that the drain is amortised.
+        int pinned = 0;
+        (void)stst_host_is_pinned(host_ptr, &pinned);
+        const std::size_t budget = pinned ? staging_bytes : 4 * staging_bytes;
         const std::size_t row_bytes = std::max<std::size_t>(width * sizeof(Cell), 1);
-        return std::max<std::size_t>(1, std::min<std::size_t>(height, staging_bytes / row_bytes));
+        return std::max<std::size_t>(1, std::min<std::size_t>(height, budget / row_bytes));
     }
 
-    void upload() {
+    void upload() { transfer_to_device(host); }
+    void download() { transfer_to_host(host); }
+
+  public:
+    /**
+     * Overwrite the device planes with the dense row-major array of whole cells at `src` (any host
+     * memory: pinned memory is read by DMA directly, anything else through the runtime's staged
+     * pipeline, stst_memcpy_2d_auto). Returns when `src` may be reused.
+     */
+    void transfer_to_device(const Cell *src) {
         if (n_cells() == 0)
             return;
+        allocate_device();
+        Cell *from = const_cast<Cell *>(src);
         if constexpr (!Layout::is_split) {
-            STST_RT_CHECK(stst_memcpy_2d_async(planes.base[0], planes.pitch[0] * sizeof(Cell), host,
-                                               width * sizeof(Cell), width * sizeof(Cell), height,
-                                               /*h2d*/ 0, stream));
+            STST_RT_CHECK(stst_memcpy_2d_auto(planes.base[0], planes.pitch[0] * sizeof(Cell), from,
+                                              width * sizeof(Cell), width * sizeof(Cell), height,
+                                              /*h2d*/ 0, device, stream));
         } else {
-            const std::size_t chunk_rows = rows_per_chunk();
+            const std::size_t chunk_rows = rows_per_chunk(src);
             void *staging[2] = {device_alloc(device, chunk_rows * width * sizeof(Cell), stream),
                                 device_alloc(device, chunk_rows * width * sizeof(Cell), stream)};
             std::size_t chunk = 0;
@@ -179,26 +204,30 @@ template <typename Cell> class GridStorage {
                 const std::size_t rows = std::min(chunk_rows, height - row);
                 const std::size_t cells = rows * width;
                 void *stage = staging[chunk & 1];
-                STST_RT_CHECK(stst_memcpy_h2d_async(stage, host + row * width, cells * sizeof(Cell),
-                                                    stream));
+                STST_RT_CHECK(stst_memcpy_2d_auto(stage, width * sizeof(Cell), from + row * width,
+                                                  width * sizeof(Cell), width * sizeof(Cell), rows,
+                                                  /*h2d*/ 0, device, stream));
                 launch_layout_kernel</*scatter=*/true>(static_cast<Cell *>(stage), row, cells);
             }
             device_free(device, staging[0], stream);
             device_free(device, staging[1], stream);
         }
-        // The caller may modify the mirror right after an accessor is gone: finish reading it now.
+        // The caller may modify the source right after this returns: finish reading it now.
         STST_RT_CHECK(stst_stream_synchronize(stream));
     }
 
-    void download() {
+    /// Copy the device planes into the dense row-major array of whole cells at `dst` (any host
+    /// memory, see transfer_to_device). Returns when `dst` holds the cells.
+    void transfer_to_host(Cell *dst) {
         if (n_cells() == 0)
             return;
+        allocate_device();
         if constexpr (!Layout::is_split) {
-            STST_RT_CHECK(stst_memcpy_2d_async(host, width * sizeof(Cell), planes.base[0],
-                                               planes.pitch[0] * sizeof(Cell), width * sizeof(Cell),
-                                               height, /*d2h*/ 1, stream));
+            STST_RT_CHECK(stst_memcpy_2d_auto(planes.base[0], planes.pitch[0] * sizeof(Cell), dst,
+                                              width * sizeof(Cell), width * sizeof(Cell), height,
+                                              /*d2h*/ 1, device, stream));
         } else {
-            const std::size_t chunk_rows = rows_per_chunk();
+            const std::size_t chunk_rows = rows_per_chunk(dst);
             void *staging[2] = {device_alloc(device, chunk_rows * width * sizeof(Cell), stream),
                                 device_alloc(device, chunk_rows * width * sizeof(Cell), stream)};
             std::size_t chunk = 0;
@@ -207,8 +236,9 @@ template <typename Cell> class GridStorage {
                 const std::size_t cells = rows * width;
                 void *stage = staging[chunk & 1];
                 launch_layout_kernel</*scatter=*/false>(static_cast<Cell *>(stage), row, cells);
-                STST_RT_CHECK(stst_memcpy_d2h_async(host + row * width, stage, cells * sizeof(Cell),
-                                                    stream));
+                STST_RT_CHECK(stst_memcpy_2d_auto(stage, width * sizeof(Cell), dst + row * width,
+                                                  width * sizeof(Cell), width * sizeof(Cell), rows,
+                                                  /*d2h*/ 1, device, stream));
             }
             device_free(device, staging[0], stream);
             device_free(device, staging[1], stream);
@@ -216,6 +246,11 @@ template <typename Cell> class GridStorage {
         STST_RT_CHECK(stst_stream_synchronize(stream));
     }
 
+    /// True if the host mirror exists and is the authoritative copy (or as current as the planes).
+    bool host_is_current() const { return host != nullptr && host_current; }
+    bool host_mirror_is_pinned() const { return host != nullptr && host_is_pinned; }
+
+  private:
     template <bool scatter>
     void launch_layout_kernel(Cell *staging, std::size_t plane_row0, std::size_t cells) {
 #if defined(__CUDACC__)
@@ -283,11 +318,25 @@ template <typename Cell> class Grid {
         if (get_grid_range() != other_buffer.get_range()) {
             throw std::range_error("The target buffer has not the same size as the grid");
         }
-        storage->allocate_host();
         sycl::host_accessor other_ac(other_buffer, sycl::read_only);
-        std::memcpy(static_cast<void *>(storage->host_data()), other_ac.get_pointer(),
-                    other_ac.byte_size());
-        storage->host_written();
+        copy_from_host(other_ac.get_pointer());
+    }
+
+    /// B200 extension: `copy_from_buffer` from a dense row-major array of height x width cells. The
+    /// cells go straight to the device (no intermediate host mirror).
+    void copy_from_host(const Cell *cells) {
+        storage->transfer_to_device(cells);
+        storage->device_written();
+    }
+
+    /// B200 extension: `copy_to_buffer` into a dense row-major array of height x width cells.
+    void copy_to_host(Cell *cells) {
+        if (storage->host_is_current()) {
+            STST_RT_CHECK(stst_host_memcpy(static_cast<void *>(cells), storage->host_data(),
+                                           storage->n_cells() * sizeof(Cell)));
+        } else {
+            storage->transfer_to_host(cells);
+        }
     }
 
     /// Overwrite the equally-sized `other_buffer` with the contents of the grid.
@@ -295,10 +344,8 @@ template <typename Cell> class Grid {
         if (get_grid_range() != other_buffer.get_range()) {
             throw std::range_error("The target buffer has not the same size as the grid");
         }
-        storage->require_host();
         sycl::host_accessor other_ac(other_buffer, sycl::write_only);
-        std::memcpy(static_cast<void *>(other_ac.get_pointer()), storage->host_data(),
-                    other_ac.byte_size());
+        copy_to_host(other_ac.get_pointer());
     }
 
     /**
@@ -359,6 +406,85 @@ template <typename Cell> class Grid {
 
     /// B200 extension: the shared state behind this handle (used by StencilUpdate).
     internal::GridStorage<Cell> &get_storage() { return *storage; }
+
+    /**
+     * B200 extension: max-norms of single fields, evaluated on the device in ONE pass over the planes
+     * involved: result[q] = max{ |cell(r, c).field_q| : r < extents[q].rows, c < extents[q].cols },
+     * -infinity for an empty extent. Replaces host loops over a `GridAccessor` such as the reference's
+     * convergence check in examples/convection/convection.cpp:412-438 (which first migrates the whole
+     * grid to the host). Waits for pending device work on the grid.
+     */
+    std::vector<double> max_abs(std::vector<FieldExtent> const &extents) {
+        std::vector<double> result(extents.size());
+        storage->require_device();
+        for (std::size_t first = 0; first < extents.size();
+             first += internal::max_field_reductions) {
+            internal::FieldReduceBatch batch{};
+            batch.n = unsigned(
+                std::min<std::size_t>(extents.size() - first, internal::max_field_reductions));
+            for (unsigned q = 0; q < batch.n; q++) {
+                FieldExtent const &e = extents[first + q];
+                batch.req[q].plane = unsigned(e.plane);
+                batch.req[q].row_lo = 0;
+                batch.req[q].row_hi = unsigned(std::min(e.rows, storage->height));
+                batch.req[q].cols = unsigned(std::min(e.cols, storage->width));
+            }
+            internal::reduce_max_abs<Cell>(storage->device, storage->stream, storage->planes, batch,
+                                           result.data() + first);
+        }
+        return result;
+    }
+
+    /// B200 extension: `max_abs` of the field `Cell::*Field` over the first `rows` x `cols` cells.
+    template <auto Field> double max_abs(std::size_t rows, std::size_t cols) {
+        return max_abs({FieldExtent{plane_of<Field>(), rows, cols}})[0];
+    }
+
+    /// B200 extension: index of the plane that stores `Cell::*Field`.
+    template <auto Field> static constexpr std::size_t plane_of() {
+        return internal::plane_of_field<Cell, Field>();
+    }
+
+    /// B200 extension: size in bytes of one element of plane `plane`.
+    static std::size_t plane_element_bytes(std::size_t plane) {
+        if (plane >= internal::CellLayout<Cell>::n_planes)
+            throw std::invalid_argument("StencilStream-B200: no such field");
+        return internal::CellLayout<Cell>::plane_bytes(plane);
+    }
+
+    /**
+     * B200 extension: copy ONE field of every cell into the dense row-major host array `dst`
+     * (height x width elements of the field's type) — `sizeof(field)` instead of `sizeof(Cell)` bytes
+     * per cell over PCIe (frame dumps: reference examples/fdtd/src/fdtd.cpp:114-166,
+     * examples/convection/convection.cpp:460-477). Returns when the copy is complete.
+     */
+    void copy_plane_to_host(std::size_t plane, void *dst) {
+        storage->require_device();
+        internal::copy_plane_rows<Cell>(storage->stream, storage->planes, plane, 0, storage->height,
+                                        storage->width, dst, /*to_device=*/false);
+        STST_RT_CHECK(stst_stream_synchronize(storage->stream));
+    }
+
+    /// B200 extension: overwrite ONE field of every cell from the dense host array `src`.
+    void copy_plane_from_host(std::size_t plane, const void *src) {
+        storage->require_device();
+        internal::copy_plane_rows<Cell>(storage->stream, storage->planes, plane, 0, storage->height,
+                                        storage->width, const_cast<void *>(src), /*to_device=*/true);
+        STST_RT_CHECK(stst_stream_synchronize(storage->stream));
+        storage->device_written();
+    }
+
+    /// B200 extension: `copy_plane_to_host` into a buffer of the field's type.
+    template <auto Field, typename T> void copy_field_to_buffer(sycl::buffer<T, 2> other_buffer) {
+        constexpr std::size_t plane = plane_of<Field>();
+        static_assert(std::is_same_v<T, typename internal::CellLayout<Cell>::template plane_t<plane>>,
+                      "buffer element type differs from the field's type");
+        if (get_grid_range() != other_buffer.get_range()) {
+            throw std::range_error("The target buffer has not the same size as the grid");
+        }
+        sycl::host_accessor other_ac(other_buffer, sycl::write_only);
+        copy_plane_to_host(plane, other_ac.get_pointer());
+    }
 
   private:
     using Storage = internal::GridStorage<Cell>;

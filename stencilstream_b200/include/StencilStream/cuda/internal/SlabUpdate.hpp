@@ -37,6 +37,7 @@
  * stencilstream_b200/sharding.py, which moves the handles with torch.distributed).
  */
 #pragma once
+#include "FieldOps.hpp"
 #include "Helpers.hpp"
 #include "Launch.hpp"
 #include "Planner.hpp"
@@ -223,6 +224,43 @@ template <typename F> class SlabUpdate {
         check_row_range(first_row, n_rows);
         join_streams();
         transfer</*to_device=*/false>(cells, first_row, n_rows);
+        STST_RT_CHECK(stst_stream_synchronize(interior_stream));
+    }
+
+    /**
+     * Max-norms of single fields over this slab's share of the extents (see Grid::max_abs): request q
+     * covers the GLOBAL rows [0, rows[q]) and columns [0, cols[q]) of plane planes[q]; out[q] is the
+     * maximum over the rows this slab owns (-infinity if it owns none of them). The caller combines
+     * the slabs' values with `max` (an all-reduce across ranks). Waits for the slab's pending work.
+     */
+    void max_abs(std::size_t n, const std::size_t *planes_idx, const std::size_t *rows,
+                 const std::size_t *cols, double *out) {
+        join_streams();
+        const PlaneSet planes = layout.planes(base, int(epoch & 1));
+        for (std::size_t first = 0; first < n; first += max_field_reductions) {
+            FieldReduceBatch batch{};
+            batch.n = unsigned(std::min<std::size_t>(n - first, max_field_reductions));
+            for (unsigned q = 0; q < batch.n; q++) {
+                const std::size_t hi = std::min(rows[first + q], cfg.row_hi);
+                batch.req[q].plane = unsigned(planes_idx[first + q]);
+                batch.req[q].row_lo = unsigned(ghost);
+                batch.req[q].row_hi = unsigned(hi > cfg.row_lo ? ghost + (hi - cfg.row_lo) : ghost);
+                batch.req[q].cols = unsigned(std::min(cols[first + q], cfg.grid_cols));
+            }
+            select_device();
+            reduce_max_abs<Cell>(cfg.device, interior_stream, planes, batch, out + first);
+        }
+    }
+
+    /// Copy ONE field of `n_rows` owned rows starting at slab-local row `first_row` into the dense
+    /// host array `dst` (n_rows x width elements of the field's type). Returns after the copy.
+    void download_plane_rows(std::size_t plane, void *dst, std::size_t first_row,
+                             std::size_t n_rows) {
+        check_row_range(first_row, n_rows);
+        join_streams();
+        select_device();
+        copy_plane_rows<Cell>(interior_stream, layout.planes(base, int(epoch & 1)), plane,
+                              ghost + first_row, n_rows, cfg.grid_cols, dst, /*to_device=*/false);
         STST_RT_CHECK(stst_stream_synchronize(interior_stream));
     }
 
@@ -419,8 +457,13 @@ template <typename F> class SlabUpdate {
         const std::size_t row_bytes = std::max<std::size_t>(width * sizeof(Cell), 1);
         if (n_rows == 0)
             return;
+        // pageable host memory moves through the runtime's staging ring, which drains per call:
+        // larger device-side chunks amortise that (see GridStorage::rows_per_chunk)
+        int pinned = 0;
+        (void)stst_host_is_pinned(cells, &pinned);
+        const std::size_t budget = std::size_t(pinned ? 64 : 256) << 20;
         const std::size_t chunk_rows =
-            std::max<std::size_t>(1, std::min<std::size_t>(n_rows, (std::size_t(64) << 20) / row_bytes));
+            std::max<std::size_t>(1, std::min<std::size_t>(n_rows, budget / row_bytes));
         void *staging[2] = {device_alloc(cfg.device, chunk_rows * width * sizeof(Cell), interior_stream),
                             device_alloc(cfg.device, chunk_rows * width * sizeof(Cell), interior_stream)};
         std::size_t chunk = 0;
@@ -433,15 +476,17 @@ template <typename F> class SlabUpdate {
                 unsigned(std::min<std::size_t>((n + block - 1) / block, std::size_t(148) * 16));
             auto s = static_cast<cudaStream_t>(interior_stream);
             if constexpr (to_device) {
-                STST_RT_CHECK(stst_memcpy_h2d_async(stage, cells + row * width, n * sizeof(Cell),
-                                                    interior_stream));
+                STST_RT_CHECK(stst_memcpy_2d_auto(stage, row_bytes, cells + row * width, row_bytes,
+                                                  row_bytes, rows, /*h2d*/ 0, cfg.device,
+                                                  interior_stream));
                 scatter_cells_kernel<Cell><<<grid, block, 0, s>>>(stage, planes, width,
                                                                   ghost + first_row + row, n);
             } else {
                 gather_cells_kernel<Cell><<<grid, block, 0, s>>>(stage, planes, width,
                                                                  ghost + first_row + row, n);
-                STST_RT_CHECK(stst_memcpy_d2h_async(cells + row * width, stage, n * sizeof(Cell),
-                                                    interior_stream));
+                STST_RT_CHECK(stst_memcpy_2d_auto(stage, row_bytes, cells + row * width, row_bytes,
+                                                  row_bytes, rows, /*d2h*/ 1, cfg.device,
+                                                  interior_stream));
             }
             if (cudaGetLastError() != cudaSuccess)
                 throw std::runtime_error("StencilStream-B200: layout kernel launch failed");

@@ -64,6 +64,10 @@ def _slab_lib(strict: bool | None = None):
         lib.stst_slab_update.argtypes = [vp, C.POINTER(_native.UpdateParams)]
         lib.stst_slab_synchronize.argtypes = [vp]
         lib.stst_slab_record_event.argtypes = [vp, vp]
+        lib.stst_slab_max_abs.argtypes = [vp, C.POINTER(_native.FieldExtent), C.c_size_t,
+                                          C.POINTER(C.c_double)]
+        lib.stst_slab_copy_field_rows_to_host.argtypes = [vp, C.c_size_t, C.c_size_t, C.c_size_t, vp,
+                                                          C.c_size_t]
         lib._slab_prototypes = True
     return lib
 
@@ -136,6 +140,23 @@ class NativeSlab:
     def exchange_halos(self) -> None:
         _check(self._lib, self._lib.stst_slab_exchange_halos(self._handle))
 
+    def max_abs(self, extents) -> list[float]:
+        """[(field, rows, cols), ...] in GLOBAL grid coordinates -> this slab's share of each
+        max-norm (-inf where it owns none of the rows)."""
+        extents = list(extents)
+        out = (C.c_double * max(len(extents), 1))()
+        _check(self._lib, self._lib.stst_slab_max_abs(
+            self._handle, _native.field_extents(self.workload, extents), len(extents), out))
+        return [float(out[q]) for q in range(len(extents))]
+
+    def field_rows_to_host(self, field, first_row: int, out: np.ndarray) -> None:
+        """ONE field of the owned rows [first_row, first_row + len(out)) (slab-local indices)."""
+        if out.dtype != _native.field_dtype(self.workload, field) or not out.flags["C_CONTIGUOUS"]:
+            raise ValueError("field_rows_to_host needs a C-contiguous array of the field's dtype")
+        _check(self._lib, self._lib.stst_slab_copy_field_rows_to_host(
+            self._handle, _native.field_index(self.workload, field), first_row, out.shape[0],
+            out.ctypes.data_as(C.c_void_p), out.nbytes))
+
     def update(self, native_params) -> None:
         _check(self._lib, self._lib.stst_slab_update(self._handle, C.byref(native_params)))
 
@@ -163,6 +184,7 @@ class ShardedStencilUpdate:
         if world > 1 and comm is None:
             raise ValueError("a process group is needed to exchange slab handles")
         self.workload, self.params = workload, params
+        self._comm = comm
         self.grid_rows, self.grid_cols = int(grid_rows), int(grid_cols)
         self.rank, self.world, self.device = rank, world, device
         self.row_lo, self.row_hi = partition_rows(self.grid_rows, world, rank)
@@ -220,6 +242,29 @@ class ShardedStencilUpdate:
         if out is None:
             out = np.empty(self.owned_shape, dtype=self.dtype)
         self.slab.copy_to_host(out)
+        return out
+
+    def max_abs(self, extents) -> list[float]:
+        """Max-norms of single fields over the WHOLE grid: [(field, rows, cols), ...] ->
+        max |cell.field| over the first rows x cols cells (global coordinates). Every slab reduces its
+        own rows on its GPU; the per-slab values are combined with an all-reduce(MAX) over the process
+        group — the only collective of the application loops (reference
+        examples/convection/convection.cpp:412-438 computes these on the host). Collective."""
+        extents = list(extents)
+        local = self.slab.max_abs(extents)
+        if self.world == 1 or not extents:
+            return local
+        import torch
+        device = "cuda" if self._comm.get_backend() == "nccl" else "cpu"
+        t = torch.tensor(local, dtype=torch.float64, device=device)
+        self._comm.all_reduce(t, op=self._comm.ReduceOp.MAX)
+        return [float(v) for v in t.cpu()]
+
+    def field_to_numpy(self, field, out: np.ndarray | None = None) -> np.ndarray:
+        """ONE field of the owned rows (single-plane download)."""
+        if out is None:
+            out = np.empty(self.owned_shape, dtype=_native.field_dtype(self.workload, field))
+        self.slab.field_rows_to_host(field, 0, out)
         return out
 
     # -- the reference's StencilUpdate surface ----------------------------------------------------------

@@ -58,6 +58,20 @@ class HostSlab:
     def copy_to_host(self, out):
         out[...] = self.cells
 
+    def max_abs(self, extents):
+        out = []
+        for field, rows, cols in extents:
+            hi = min(int(rows), self.row_hi) - self.row_lo
+            plane = self.cells[self.dtype.names[_native.field_index(self.workload, field)]] \
+                if self.dtype.names else self.cells
+            part = plane[:max(hi, 0), :int(cols)]
+            out.append(float(np.abs(part.astype(np.float64)).max()) if part.size else float("-inf"))
+        return out
+
+    def field_rows_to_host(self, field, first_row, out):
+        name = self.dtype.names[_native.field_index(self.workload, field)]
+        out[...] = self.cells[name][first_row:first_row + out.shape[0]]
+
     def exchange_halos(self):
         self.log.append("exchange")
         self._exchange()

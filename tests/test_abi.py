@@ -34,7 +34,7 @@ def test_workloads_exports_every_declared_symbol(built, strict):
     for name in names:
         assert hasattr(lib, name), f"libstst_workloads does not export {name}"
     assert sorted(_native.WORKLOADS_SYMBOLS) == names
-    assert lib.stst_workloads_abi_version() == 1
+    assert lib.stst_workloads_abi_version() == 2
 
 
 def test_registry_matches_the_python_mirror(built):
@@ -92,3 +92,22 @@ def test_product_package_never_imports_the_oracle():
             continue
         text = path.read_text()
         assert "import oracle" not in text and "liboracle" not in text, path
+
+
+def test_host_copy_workers_copy_exactly(built):
+    """stst_host_memcpy (the multi-threaded host copy behind the staged transfer pipeline) is a
+    memcpy: odd sizes, sizes below and above the threading threshold, unaligned ends."""
+    import numpy as np
+    rt = _native.runtime_lib()
+    rt.stst_host_memcpy.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    rng = np.random.default_rng(0)
+    for n in (0, 1, 4095, (4 << 20) - 1, (4 << 20) + 1, 37_000_003):
+        src = rng.integers(0, 256, size=n + 16, dtype=np.uint8)
+        dst = np.zeros(n + 16, dtype=np.uint8)
+        assert rt.stst_host_memcpy(dst.ctypes.data + 3, src.ctypes.data + 5, n) == 0
+        assert dst[3:3 + n].tobytes() == src[5:5 + n].tobytes()
+        assert not dst[:3].any() and not dst[3 + n:].any()
+    pinned = C.c_int(-1)
+    probe = np.zeros(16, dtype=np.uint8)
+    assert rt.stst_host_is_pinned(probe.ctypes.data_as(C.c_void_p), C.byref(pinned)) == 0
+    assert pinned.value == 0

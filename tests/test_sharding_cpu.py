@@ -79,6 +79,15 @@ def _worker(rank, world, port, workload, shape, offset, n, depth, failures, mode
         update.get_params().n_iterations = 2
         update()
         mine = update.to_numpy()
+        # per-field device operations: max-norms over the whole grid (collective) and a single-field
+        # download of the owned rows
+        names = mine.dtype.names or (0,)
+        extents = [(f, shape[0] - 1 - (i % 2), shape[1] - (i % 3)) for i, f in enumerate(names)]
+        norms = update.max_abs(extents)
+        if mine.dtype.names:
+            last = names[-1]
+            if update.field_to_numpy(last).tobytes() != np.ascontiguousarray(mine[last]).tobytes():
+                failures.put(f"{workload}: single-field download differs from the cells' field")
         gathered = [None] * world
         dist.all_gather_object(gathered, (lo, hi, mine.tobytes()))
         if rank == 0:
@@ -86,6 +95,11 @@ def _worker(rank, world, port, workload, shape, offset, n, depth, failures, mode
             got = np.empty_like(want)
             for glo, ghi, raw in gathered:
                 got[glo:ghi] = np.frombuffer(raw, dtype=want.dtype).reshape(ghi - glo, shape[1])
+            for (f, r, c), norm in zip(extents, norms):
+                plane = want[f] if want.dtype.names else want
+                expect_norm = float(np.abs(plane[:r, :c].astype(np.float64)).max())
+                if norm != expect_norm:
+                    failures.put(f"{workload}: max_abs({f}, {r}, {c}) = {norm!r}, oracle {expect_norm!r}")
             if got.tobytes() != want.tobytes():
                 bad = np.argwhere(got.view(np.uint8).reshape(shape[0], -1)
                                   != want.view(np.uint8).reshape(shape[0], -1))
