@@ -454,13 +454,16 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             timer.sync()
             t0 = time.perf_counter()
             result = e2e_update(host_grid)          # H2D upload + layout + all fused launches
-            mid = result.accessor("read")[rows // 2, cols // 2]  # D2H of the whole result grid
-            images_pinned = (host_grid.host_image_is_pinned(), result.host_image_is_pinned())
+            view = result.accessor("read")          # D2H of the whole result grid
+            mid = view[rows // 2, cols // 2]
             checksum = float(mid[dtype.names[0]] if dtype.names else mid)
             t1 = time.perf_counter()
+            images_pinned = (host_grid.host_image_is_pinned(), result.host_image_is_pinned())
             if i > 0:
                 times.append(t1 - t0)
-            del result
+            # `mid` of a struct cell is a numpy.void that references the accessor view, which keeps the
+            # result grid and its pinned image alive: drop all of them before the next step allocates
+            del mid, view, result
         e2e_value = total_cells * iters / float(np.mean(times)) / 1e9
         e2e = {"value": e2e_value, "unit": "GCell-updates/s",
                "h2d_bytes_per_step": int(rows * cols * dtype.itemsize),

@@ -25,6 +25,9 @@
 
 #include <algorithm>
 #include <cstdlib>
+#if defined(__linux__)
+    #include <sys/mman.h>
+#endif
 #include <cstring>
 #include <memory>
 #include <stdexcept>
@@ -119,9 +122,15 @@ template <typename Cell> class GridStorage {
         } else {
             // The machine refuses to pin that much memory: an ordinary (pageable) mirror still
             // works, transfers are just staged by the driver and slower.
-            p = std::aligned_alloc(4096, (bytes + 4095) / 4096 * 4096);
+            // 2 MiB alignment + MADV_HUGEPAGE: a fresh gigabyte image otherwise takes a page fault
+            // per 4 KiB the first time a download writes it.
+            constexpr std::size_t huge = std::size_t(2) << 20;
+            p = std::aligned_alloc(huge, (bytes + huge - 1) / huge * huge);
             if (!p)
                 throw std::bad_alloc();
+#if defined(__linux__) && defined(MADV_HUGEPAGE)
+            (void)madvise(p, (bytes + huge - 1) / huge * huge, MADV_HUGEPAGE);
+#endif
             host_is_pinned = false;
         }
         host = static_cast<Cell *>(p);
@@ -460,7 +469,7 @@ template <typename Cell> class Grid {
      */
     void copy_plane_to_host(std::size_t plane, void *dst) {
         storage->require_device();
-        internal::copy_plane_rows<Cell>(storage->stream, storage->planes, plane, 0, storage->height,
+        internal::copy_plane_rows<Cell>(storage->device, storage->stream, storage->planes, plane, 0, storage->height,
                                         storage->width, dst, /*to_device=*/false);
         STST_RT_CHECK(stst_stream_synchronize(storage->stream));
     }
@@ -468,7 +477,7 @@ template <typename Cell> class Grid {
     /// B200 extension: overwrite ONE field of every cell from the dense host array `src`.
     void copy_plane_from_host(std::size_t plane, const void *src) {
         storage->require_device();
-        internal::copy_plane_rows<Cell>(storage->stream, storage->planes, plane, 0, storage->height,
+        internal::copy_plane_rows<Cell>(storage->device, storage->stream, storage->planes, plane, 0, storage->height,
                                         storage->width, const_cast<void *>(src), /*to_device=*/true);
         STST_RT_CHECK(stst_stream_synchronize(storage->stream));
         storage->device_written();

@@ -207,24 +207,21 @@ inline void reduce_max_abs(int device, stst_stream_t stream, PlaneSet const &pla
 
 /**
  * Copy plane rows [row_lo, row_lo + n_rows) x [0, cols) of plane `plane` into the dense row-major
- * host array `dst` (to_device = false) or the other way round. Asynchronous on `stream`.
+ * host array `host` (to_device = false) or the other way round. In order on `stream`; the caller
+ * synchronises the stream before it uses `host` (a pinned `host` is copied asynchronously).
  */
 template <typename Cell>
-inline void copy_plane_rows(stst_stream_t stream, PlaneSet const &planes, std::size_t plane,
-                            std::size_t row_lo, std::size_t n_rows, std::size_t cols, void *host,
-                            bool to_device) {
+inline void copy_plane_rows(int device, stst_stream_t stream, PlaneSet const &planes,
+                            std::size_t plane, std::size_t row_lo, std::size_t n_rows,
+                            std::size_t cols, void *host, bool to_device) {
     if (plane >= CellLayout<Cell>::n_planes)
         throw std::invalid_argument("StencilStream-B200: no such field");
     const std::size_t elem = CellLayout<Cell>::plane_bytes(plane);
     const std::size_t pitch_bytes = planes.pitch[plane] * elem;
     unsigned char *dev = static_cast<unsigned char *>(planes.base[plane]) + row_lo * pitch_bytes;
-    if (to_device) {
-        STST_RT_CHECK(stst_memcpy_2d_async(dev, pitch_bytes, host, cols * elem, cols * elem, n_rows,
-                                           /*h2d*/ 0, stream));
-    } else {
-        STST_RT_CHECK(stst_memcpy_2d_async(host, cols * elem, dev, pitch_bytes, cols * elem, n_rows,
-                                           /*d2h*/ 1, stream));
-    }
+    // pinned host memory: one strided DMA; anything else: the runtime's staged pipeline
+    STST_RT_CHECK(stst_memcpy_2d_auto(dev, pitch_bytes, host, cols * elem, cols * elem, n_rows,
+                                      to_device ? 0 : 1, device, stream));
 }
 
 /// Index of the plane that stores `Cell::*Field`, for cells with a `fields` list.

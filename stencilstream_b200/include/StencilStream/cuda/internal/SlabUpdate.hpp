@@ -259,7 +259,7 @@ template <typename F> class SlabUpdate {
         check_row_range(first_row, n_rows);
         join_streams();
         select_device();
-        copy_plane_rows<Cell>(interior_stream, layout.planes(base, int(epoch & 1)), plane,
+        copy_plane_rows<Cell>(cfg.device, interior_stream, layout.planes(base, int(epoch & 1)), plane,
                               ghost + first_row, n_rows, cfg.grid_cols, dst, /*to_device=*/false);
         STST_RT_CHECK(stst_stream_synchronize(interior_stream));
     }

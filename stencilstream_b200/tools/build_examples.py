@@ -37,7 +37,20 @@ EXAMPLES = {
     "hotspot": ("hotspot.cpp", ["-DHOTSPOT_SPLIT_CELL_STRUCT=1"], False),
     "fdtd": ("src/fdtd.cpp", ["-DMATERIAL=0", "-DTDVS_TYPE=0", "-DFDTD_SPLIT_CELL_STRUCT=1"], True),
     "convection": ("convection.cpp", ["-DCONVECTION_SPIT_CELL_STRUCT=1"], True),
+    # the other material resolvers / TDV strategies of examples/fdtd/CMakeLists.txt:14-40: a functor
+    # that carries a 16-entry coefficient table by value and indexes it per cell (lut), or searches
+    # it by distance (render); cells with an ac_int member (lut: not plane-splittable, stays AoS)
+    "fdtd_lut": ("src/fdtd.cpp", ["-DMATERIAL=1", "-DTDVS_TYPE=1", "-DFDTD_SPLIT_CELL_STRUCT=1"], True,
+                 "fdtd"),
+    "fdtd_render": ("src/fdtd.cpp", ["-DMATERIAL=2", "-DTDVS_TYPE=2", "-DFDTD_SPLIT_CELL_STRUCT=1"],
+                    True, "fdtd"),
 }
+
+
+def example_dir_name(name: str) -> str:
+    """Directory under the reference's examples/ that holds the sources of example `name`."""
+    entry = EXAMPLES[name]
+    return entry[3] if len(entry) > 3 else name
 
 
 def stage_sources(example_dir: Path, out_dir: Path) -> int:
@@ -52,8 +65,8 @@ def stage_sources(example_dir: Path, out_dir: Path) -> int:
 
 def build_example(name: str, source_root: Path, out_root: Path, backend: str = "b200",
                   verbose: bool = True) -> Path:
-    main_rel, macros, needs_json = EXAMPLES[name]
-    example_dir = source_root / name
+    main_rel, macros, needs_json = EXAMPLES[name][:3]
+    example_dir = source_root / example_dir_name(name)
     if not example_dir.exists():
         raise FileNotFoundError(f"{example_dir} not found")
     pkg = ROOT / "stencilstream_b200"
@@ -108,7 +121,7 @@ def case_commands(name: str, case_dir: Path, binary: Path, out_dir: Path):
     if name == "hotspot":
         return [str(binary), "200", "264", "100", str(case_dir / "temp.bin"),
                 str(case_dir / "power.bin"), str(out_dir / "out.bin")], None
-    if name == "fdtd":
+    if name.startswith("fdtd"):
         return [str(binary), "-c", str(case_dir / "experiment.json"), "-o", str(out_dir)], None
     if name == "convection":
         return [str(binary), str(case_dir / "experiment.json"), str(out_dir)], None
@@ -134,7 +147,7 @@ def stage_case(name: str, case_dir: Path) -> None:
         cells["temp"] += rng.random(cells.shape).astype(np.float32) * 40
         cells["temp"].astype("<f4").tofile(case_dir / "temp.bin")
         cells["power"].astype("<f4").tofile(case_dir / "power.bin")
-    elif name == "fdtd":
+    elif name.startswith("fdtd"):
         cfg = json.loads(json.dumps(W.FDTD_DEFAULT))
         cfg["time"] = {"t_cutoff": 7.0, "t_detect": 0.05, "t_max": 0.25, "t_snap": 0.1}
         (case_dir / "experiment.json").write_text(json.dumps(cfg, indent=1))

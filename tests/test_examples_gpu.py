@@ -38,7 +38,7 @@ def _strip_timing(text):
     return "\n".join(keep)
 
 
-@pytest.mark.parametrize("name", ["conway", "hotspot", "fdtd", "convection"])
+@pytest.mark.parametrize("name", ["conway", "hotspot", "fdtd", "fdtd_lut", "fdtd_render", "convection"])
 def test_example_output_equals_reference_cpu_backend(name, tmp_path):
     binary = _binary(name)
     case_dir = OUT / "cases" / name
