@@ -178,9 +178,15 @@ class Grid:
             self._handle, _native.field_extents(self.workload, extents), len(extents), out))
         return [float(out[q]) for q in range(len(extents))]
 
-    def field_to_numpy(self, field) -> np.ndarray:
-        """ONE field of every cell as a dense 2-D array (single-plane download)."""
-        out = np.empty(self.get_grid_range(), dtype=_native.field_dtype(self.workload, field))
+    def field_to_numpy(self, field, out: np.ndarray | None = None) -> np.ndarray:
+        """ONE field of every cell as a dense 2-D array (single-plane download), optionally into the
+        C-contiguous array `out` (a reused destination avoids first-touch page faults)."""
+        dtype = _native.field_dtype(self.workload, field)
+        if out is None:
+            out = np.empty(self.get_grid_range(), dtype=dtype)
+        elif (out.dtype != dtype or tuple(out.shape) != self.get_grid_range()
+              or not out.flags["C_CONTIGUOUS"]):
+            raise RangeError("The target buffer has not the same size as the grid")
         _check(self._lib, self._lib.stst_grid_copy_field_to_host(
             self._handle, _native.field_index(self.workload, field),
             out.ctypes.data_as(C.c_void_p), out.nbytes))

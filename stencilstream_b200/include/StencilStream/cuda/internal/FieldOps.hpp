@@ -69,12 +69,23 @@ inline double max_abs_from_key(unsigned long long key) {
     return v;
 }
 
-/// True if plane `plane` of `Cell` holds an arithmetic type (and can therefore be reduced).
+/// Types a plane may hold for `reduce_max_abs`: arithmetic types, and enumerations (by their value).
+template <typename T>
+inline constexpr bool is_reducible_v = std::is_arithmetic_v<T> || std::is_enum_v<T>;
+
+template <typename T> STST_HD constexpr double reducible_to_double(T const &v) {
+    if constexpr (std::is_enum_v<T>)
+        return double(static_cast<std::underlying_type_t<T>>(v));
+    else
+        return double(v);
+}
+
+/// True if plane `plane` of `Cell` holds such a type.
 template <typename Cell> bool plane_is_arithmetic(std::size_t plane) {
     bool result = false;
     for_each_plane<Cell>([&](auto I) {
         if (plane == I)
-            result = std::is_arithmetic_v<typename CellLayout<Cell>::template plane_t<I>>;
+            result = is_reducible_v<typename CellLayout<Cell>::template plane_t<I>>;
     });
     return result;
 }
@@ -100,7 +111,7 @@ __global__ void __launch_bounds__(reduce_block_threads)
         double m = -1.0; // below every |v|; "nothing seen" if it survives
         for_each_plane<Cell>([&](auto I) {
             using T = typename L::template plane_t<I>;
-            if constexpr (std::is_arithmetic_v<T>) {
+            if constexpr (is_reducible_v<T>) {
                 if (rq.plane != I)
                     return;
                 constexpr unsigned V = sizeof(T) >= 16 ? 1u : unsigned(16 / sizeof(T));
@@ -119,7 +130,7 @@ __global__ void __launch_bounds__(reduce_block_threads)
 #pragma unroll
                         for (unsigned j = 0; j < V; j++) {
                             if (i * V + j < rq.cols) {
-                                double a = double(x.v[j]);
+                                double a = reducible_to_double(x.v[j]);
                                 a = a < 0.0 ? -a : a;
                                 if (a > m)
                                     m = a;

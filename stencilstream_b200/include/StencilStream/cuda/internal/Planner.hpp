@@ -74,7 +74,7 @@ template <typename Cell> constexpr int column_group_width() {
     if (widest >= 8)
         return 2;
 #if defined(STST_LIGHT_COLUMN_GROUP_WIDTH)
-    if (sizeof(Cell) <= 8 && widest == 4)
+    if (CellLayout<Cell>::n_planes == 1 && widest == 4)
         return STST_LIGHT_COLUMN_GROUP_WIDTH;
 #endif
     return 4;
@@ -92,7 +92,8 @@ template <typename Cell> constexpr int max_threads_per_cta() {
 /// blockDim.x the sweep kernel is compiled for, or 0 if it is a run-time choice. Cells that use
 /// lane-major tiles (TileKernel.hpp) get a fixed 64 so that their sub-row offsets are immediates.
 template <typename Cell> constexpr int fixed_block_x() {
-    return lane_major_tiles<Cell, column_group_width<Cell>()>() ? 64 : 0;
+    // 256 staged columns per tile row: 64 threads x 4 columns, or 32 x 8
+    return lane_major_tiles<Cell, column_group_width<Cell>()>() ? 256 / column_group_width<Cell>() : 0;
 }
 
 /// Whether every plane of `Cell` can be staged by a TMA box load.

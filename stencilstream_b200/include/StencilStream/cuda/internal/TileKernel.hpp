@@ -69,7 +69,7 @@ template <typename Cell, int CW> constexpr bool lane_major_tiles() {
     return false;
 #else
     using L = CellLayout<Cell>;
-    return CW == 4 && L::n_planes == 1 && L::plane_bytes(0) == 4;
+    return (CW == 4 || CW == 8) && L::n_planes == 1 && L::plane_bytes(0) == 4;
 #endif
 }
 
@@ -432,7 +432,16 @@ sweep_rows(F const &tf, typename F::Cell const &halo_value,
     if (y_begin >= y_end)
         return;
 
-    Cell win[D][WC];
+    // window_reload may produce several output rows per step from ONE (D + rows - 1)-row window: the
+    // rows share D - 1 window rows (fewer shared-memory loads), and their functor evaluations are
+    // independent instruction streams the scheduler can interleave (latency-bound fat functors).
+#if defined(STST_RELOAD_ROWS)
+    constexpr int RPS = (kMode == window_reload) ? STST_RELOAD_ROWS : 1;
+#else
+    constexpr int RPS = 1;
+#endif
+    constexpr int DW = D + RPS - 1;
+    Cell win[DW][WC];
 
     // Load tile row `row`, columns [c0 - R, c0 + CW + R), into `w`.
     auto load_row = [&](Cell(&w)[WC], int row) {
@@ -508,7 +517,7 @@ sweep_rows(F const &tf, typename F::Cell const &halo_value,
                 for (int sr = 0; sr < D; sr++) {
 #pragma unroll
                     for (int sc = 0; sc < D; sc++) {
-                        st[sycl::id<2>(sr, sc)] = win[(top + sr) % D][i + sc];
+                        st[sycl::id<2>(sr, sc)] = win[(top + sr) % DW][i + sc];
                     }
                 }
                 result[i] = tf(st);
@@ -581,7 +590,18 @@ sweep_rows(F const &tf, typename F::Cell const &halo_value,
     }
 
     if constexpr (kMode == window_reload) {
-        for (int y = y_begin; y < y_end; y++) {
+        int y = y_begin;
+        if constexpr (RPS > 1) {
+            for (; y + RPS <= y_end; y += RPS) {
+#pragma unroll
+                for (int j = 0; j < DW; j++)
+                    load_row(win[j], y - R + j);
+                [&]<int... Us>(std::integer_sequence<int, Us...>) {
+                    (compute_row(std::integral_constant<int, Us>{}, y + Us), ...);
+                }(std::make_integer_sequence<int, RPS>{});
+            }
+        }
+        for (; y < y_end; y++) {
 #pragma unroll
             for (int j = 0; j < D; j++)
                 load_row(win[j], y - R + j);

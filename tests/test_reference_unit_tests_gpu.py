@@ -24,3 +24,15 @@ def test_reference_cuda_unit_tests_pass():
     assert len(passed) >= 8, proc.stdout
     assert any("cuda::StencilUpdate (Split cell structure)" in line for line in passed)
     assert any("cuda::Grid::copy_to_buffer" in line for line in passed)
+
+
+def test_own_cpp_tests_of_the_grid_extensions_pass():
+    """tests/cpp/grid_extensions.cu: Grid::max_abs, single-field copies, copies from/to ordinary host
+    memory, through the C++ template API (built by build_reference_tests.build_own)."""
+    binary = BINARY.parent.parent / "own_tests" / "unit_test_extensions_b200"
+    if not binary.exists():
+        pytest.skip(f"{binary} not built")
+    proc = subprocess.run([str(binary)], capture_output=True, text=True, timeout=600)
+    print(proc.stdout)
+    assert proc.returncode == 0, proc.stdout + proc.stderr
+    assert sum(line.startswith("[ OK ]") for line in proc.stdout.splitlines()) == 4
