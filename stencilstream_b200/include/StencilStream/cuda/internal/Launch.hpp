@@ -113,6 +113,7 @@ template <typename F> struct SweepLauncher {
         geo.tiles_x = (geo.grid_w + geo.tile_w - 1) / geo.tile_w;
         geo.use_tma = plan.use_tma ? 1u : 0u;
         geo.push = push ? 1u : 0u;
+        geo.inv_block_y = (1u << 24) / plan.block_y + 1u;
         geo.iteration0 = iteration0;
         const unsigned out_rows = unsigned(region.out_row_hi - region.out_row_lo);
         const unsigned tiles_y = (out_rows + geo.tile_h - 1) / geo.tile_h;
