@@ -215,6 +215,10 @@ typedef struct stst_update_stats {
     size_t n_launches;     /* fused kernel launches so far                    */
     unsigned fused_iterations, tile_h, tile_w, block_x, block_y, use_tma;
     size_t smem_bytes;
+    /* speculative plane pass-through: planes (bit i = field i) the tile sweeps currently leave in
+     * place instead of copying them, and how many updates had to be repeated because one changed */
+    unsigned passthrough_planes;
+    size_t speculation_redos;
 } stst_update_stats;
 
 int stst_update_create(const char *workload, const stst_update_params *params, stst_update **update);

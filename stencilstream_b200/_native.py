@@ -88,7 +88,7 @@ class UpdateStats(C.Structure):
         ("n_processed_cells", C.c_size_t), ("walltime", C.c_double), ("kernel_runtime", C.c_double),
         ("n_launches", C.c_size_t), ("fused_iterations", C.c_uint), ("tile_h", C.c_uint),
         ("tile_w", C.c_uint), ("block_x", C.c_uint), ("block_y", C.c_uint), ("use_tma", C.c_uint),
-        ("smem_bytes", C.c_size_t),
+        ("smem_bytes", C.c_size_t), ("passthrough_planes", C.c_uint), ("speculation_redos", C.c_size_t),
     ]
 
 

@@ -159,6 +159,8 @@ template <typename F, typename ParamBlock> struct UpdateHolder final : UpdateBas
         s.block_y = plan.block_y;
         s.use_tma = plan.use_tma ? 1u : 0u;
         s.smem_bytes = plan.smem_bytes;
+        s.passthrough_planes = update->get_passthrough_planes();
+        s.speculation_redos = update->get_n_speculation_redos();
     }
 };
 

@@ -21,6 +21,10 @@
  *
  * What is different: instead of one launch per sweep, ceil(n_iterations / k) launches of the fused,
  * shared-memory-tiled kernel in cuda/internal/TileKernel.hpp, planned by cuda/internal/Planner.hpp.
+ * Fields that a transition function only passes through (HotSpot's `power`, FDTD's material
+ * coefficients) are detected at run time and no longer copied between the tile buffers — speculative
+ * plane pass-through, verified by every launch and transparently repeated without the speculation if a
+ * launch ever sees such a field change (see `run_speculative` below and run_tile in TileKernel.hpp).
  * `split_cell_structure` is accepted for source compatibility; the device layout is decided by
  * `Grid<Cell>` from `Cell::fields` alone (planes whenever the cell lists its fields), so both
  * values select the same code path and produce the same results.
@@ -35,6 +39,7 @@
 #include "internal/Runtime.hpp"
 #include "internal/TileKernel.hpp"
 
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -99,6 +104,17 @@ template <concepts::TransitionFunction F, bool split_cell_structure = false> cla
         : params(params), n_processed_cells(0), walltime(0.0), n_launches(0), last_plan(),
           tensor_maps(), profile_events() {}
 
+    StencilUpdate(StencilUpdate const &other)
+        : params(other.params), n_processed_cells(other.n_processed_cells),
+          walltime(other.walltime), n_launches(other.n_launches), last_plan(other.last_plan),
+          tensor_maps(), profile_events(other.profile_events) {}
+    StencilUpdate &operator=(StencilUpdate const &) = delete;
+
+    ~StencilUpdate() {
+        if (spec_flags)
+            internal::device_free(spec_device, spec_flags, internal::default_stream(spec_device));
+    }
+
     /**
      * Compute `n_iterations` iterations of the source grid and return the result as a new grid.
      * The source grid is not modified.
@@ -149,10 +165,189 @@ template <concepts::TransitionFunction F, bool split_cell_structure = false> cla
     /// B200 extension: the plan used by the most recent call.
     internal::LaunchPlan const &get_last_plan() const { return last_plan; }
 
+    /// B200 extension: planes (bit i = plane i) that currently pass through every sub-iteration
+    /// without being copied (speculative plane pass-through), and how many times an update had to
+    /// be repeated because a launch saw such a plane change.
+    unsigned get_passthrough_planes() const {
+        if (!spec_probed)
+            return 0;
+        unsigned m = all_planes;
+        for (unsigned q = 0; q < n_sub; q++)
+            m &= spec_keep[q];
+        return m;
+    }
+    std::size_t get_n_speculation_redos() const { return n_spec_redos; }
+
   private:
+    static constexpr unsigned n_sub = unsigned(F::n_subiterations);
+    static constexpr unsigned all_planes =
+        Layout::n_planes >= 32 ? ~0u : ((1u << Layout::n_planes) - 1u);
+
+    static bool speculation_enabled() {
+        if constexpr (!internal::speculation_capable<F>())
+            return false;
+        static const bool enabled = internal::env_long("STST_SPECULATE", 1) != 0;
+        return enabled;
+    }
+
+    /**
+     * The generation loop with speculative plane pass-through.
+     *
+     * The first launch this updater ever submits also *observes*: per sub-iteration, which planes
+     * came out of the transition function different from the centre cell that went in. Planes that
+     * never changed are from then on left in place by the tile sweeps instead of being copied from
+     * tile buffer to tile buffer, and planes untouched in every sub-iteration need only one tile
+     * buffer, so the tiles grow. Every launch still compares what the function returned for those
+     * planes with what went in (for a genuinely passed-through field the compiler folds that away)
+     * and reports any difference through a device flag, which is read when all launches of the call
+     * have been submitted. If a launch reports a difference — the field does change after all, e.g.
+     * FDTD's `hz_sum` once `iteration >= detect_iteration` — that plane is struck from the masks and
+     * the WHOLE call is repeated from the (never modified) source grid. The result is therefore
+     * always what the unspeculated loop computes; the price is that such calls end with a stream
+     * synchronisation even when `blocking` is false.
+     */
+    GridImpl run_speculative(GridImpl &source_grid) {
+        using namespace internal;
+        auto &source = source_grid.get_storage();
+        const unsigned grid_h = unsigned(source.height), grid_w = unsigned(source.width);
+        source.require_device();
+        if (spec_flags && spec_device != source.device) {
+            device_free(spec_device, spec_flags, default_stream(spec_device));
+            spec_flags = nullptr;
+        }
+        if (!spec_flags) {
+            spec_device = source.device;
+            spec_flags = static_cast<unsigned *>(
+                device_alloc(spec_device, sizeof(unsigned) * (max_spec_subiterations + 1),
+                             source.stream));
+        }
+        unsigned *host_flags =
+            static_cast<unsigned *>(pinned_alloc(sizeof(unsigned) * (max_spec_subiterations + 1)));
+        auto read_flags = [&] {
+            STST_RT_CHECK(stst_memcpy_d2h_async(host_flags, spec_flags,
+                                                sizeof(unsigned) * (max_spec_subiterations + 1),
+                                                source.stream));
+            STST_RT_CHECK(stst_stream_synchronize(source.stream));
+        };
+        auto clear_flags = [&] {
+            STST_RT_CHECK(stst_memset_async(spec_flags, 0,
+                                            sizeof(unsigned) * (max_spec_subiterations + 1),
+                                            source.stream));
+        };
+
+        try {
+            for (;;) {
+                clear_flags();
+                GridImpl swap_a = source_grid.make_similar();
+                GridImpl swap_b = source_grid.make_similar();
+                swap_a.get_storage().allocate_device();
+                GridImpl *pass_source = &source_grid, *pass_target = &swap_a;
+                std::size_t iteration = params.iteration_offset;
+                std::size_t remaining = params.n_iterations;
+                bool first = true;
+                auto advance = [&](LaunchPlan const &plan, Speculation const &spec) {
+                    const unsigned n_gens =
+                        unsigned(std::min<std::size_t>(remaining, plan.fused_iterations));
+                    pass_target->get_storage().allocate_device();
+                    launch(plan, pass_source->get_storage(), pass_target->get_storage(), iteration,
+                           n_gens, &spec);
+                    iteration += n_gens;
+                    remaining -= n_gens;
+                    if (first) {
+                        pass_source = &swap_a;
+                        pass_target = &swap_b;
+                        first = false;
+                    } else {
+                        std::swap(pass_source, pass_target);
+                    }
+                };
+
+                if (!spec_probed) {
+                    // observe with the unspeculated plan, then read what changed
+                    const LaunchPlan plan0 = make_plan<F>(source.device, grid_h, grid_w,
+                                                          params.n_iterations,
+                                                          params.fused_iterations, params.tile_rows);
+                    Speculation observe{};
+                    observe.probe = true;
+                    observe.flags = spec_flags;
+                    advance(plan0, observe);
+                    last_plan = plan0;
+                    read_flags();
+                    for (unsigned q = 0; q < n_sub; q++)
+                        spec_keep[q] = ~host_flags[q] & all_planes;
+                    spec_probed = true;
+                    drop_unprofitable_speculation();
+                    clear_flags();
+                }
+
+                Speculation spec{};
+                for (unsigned q = 0; q < n_sub; q++)
+                    spec.keep[q] = spec_keep[q];
+                spec.flags = spec_flags;
+                if (remaining > 0) {
+                    const LaunchPlan plan = make_plan<F>(
+                        source.device, grid_h, grid_w, params.n_iterations, params.fused_iterations,
+                        params.tile_rows, spec.single_planes(n_sub, all_planes));
+                    last_plan = plan;
+                    while (remaining > 0)
+                        advance(plan, spec);
+                }
+                read_flags();
+                const unsigned violated = host_flags[max_spec_subiterations];
+                if (violated == 0) {
+                    pass_source->get_storage().device_written();
+                    pinned_free(host_flags);
+                    return *pass_source;
+                }
+                // A plane believed to pass through did change: never speculate on it again and
+                // recompute this call from the untouched source grid.
+                for (unsigned q = 0; q < n_sub; q++)
+                    spec_keep[q] &= ~violated;
+                drop_unprofitable_speculation();
+                n_spec_redos++;
+            }
+        } catch (...) {
+            pinned_free(host_flags);
+            throw;
+        }
+    }
+
+    /// Pass-through pays through the planes that need only ONE tile buffer (taller tiles) and the
+    /// stores it saves; the kernels that support it carry per-plane buffer bookkeeping, which costs
+    /// registers. Measured (profiles/r01_s3_sweep_speculation.log): HotSpot +11 %, FDTD +19 % with
+    /// half of the cell passing through, mantle convection -11 % with one field of eleven. Below a
+    /// quarter of the cell's bytes the unspeculated kernels are used.
+    void drop_unprofitable_speculation() {
+        unsigned single = all_planes;
+        for (unsigned q = 0; q < n_sub; q++)
+            single &= spec_keep[q];
+        std::size_t bytes = 0;
+        for (std::size_t i = 0; i < Layout::n_planes; i++)
+            if ((single >> i) & 1u)
+                bytes += Layout::plane_bytes(i);
+        if (4 * bytes < sizeof(Cell)) {
+            for (unsigned q = 0; q < n_sub; q++)
+                spec_keep[q] = 0;
+        }
+    }
+
+    bool speculation_has_nothing_left() const {
+        if (!spec_probed)
+            return false;
+        for (unsigned q = 0; q < n_sub; q++)
+            if (spec_keep[q] != 0)
+                return false;
+        return true;
+    }
+
     GridImpl run_simulation(GridImpl &source_grid) {
         if (params.n_iterations == 0) {
             return source_grid;
+        }
+        if constexpr (internal::speculation_capable<F>()) {
+            if (speculation_enabled() && !speculation_has_nothing_left() &&
+                source_grid.get_grid_height() > 0 && source_grid.get_grid_width() > 0)
+                return run_speculative(source_grid);
         }
 
         auto &source = source_grid.get_storage();
@@ -213,7 +408,8 @@ template <concepts::TransitionFunction F, bool split_cell_structure = false> cla
     }
 
     void launch(internal::LaunchPlan const &plan, internal::GridStorage<Cell> &src,
-                internal::GridStorage<Cell> &dst, std::size_t iteration0, unsigned n_gens) {
+                internal::GridStorage<Cell> &dst, std::size_t iteration0, unsigned n_gens,
+                internal::Speculation const *spec = nullptr) {
         using namespace internal;
         LaunchRegion region{};
         region.device = src.device;
@@ -234,7 +430,7 @@ template <concepts::TransitionFunction F, bool split_cell_structure = false> cla
 
         SweepLauncher<F>::launch(plan, params.transition_function, params.halo_value, src.planes,
                                  dst.planes, nullptr, region, iteration0, n_gens, tensor_maps,
-                                 src.stream);
+                                 src.stream, spec);
         n_launches++;
 
         if (params.profiling) {
@@ -251,6 +447,12 @@ template <concepts::TransitionFunction F, bool split_cell_structure = false> cla
     internal::TensorMapCache<Cell> tensor_maps;
     std::vector<std::pair<std::shared_ptr<internal::Event>, std::shared_ptr<internal::Event>>>
         profile_events;
+    // speculative plane pass-through (run_speculative)
+    bool spec_probed = false;
+    unsigned spec_keep[internal::max_spec_subiterations] = {};
+    unsigned *spec_flags = nullptr;
+    int spec_device = 0;
+    std::size_t n_spec_redos = 0;
 };
 
 } // namespace cuda

@@ -67,6 +67,32 @@ template <typename Cell> class TensorMapCache {
     std::map<Key, TensorMapSet> cache;
 };
 
+/**
+ * Host-side state of speculative plane pass-through for one updater (see run_tile in
+ * TileKernel.hpp): per sub-iteration, the planes a launch may leave in place instead of copying
+ * them from tile buffer to tile buffer, and the device words through which the kernels report what
+ * they observed.
+ */
+struct Speculation {
+    unsigned keep[max_spec_subiterations] = {};
+    bool probe = false;          ///< the launch only observes (keep must be all-zero)
+    unsigned *flags = nullptr;   ///< device: [0, S) changed per sub-iteration, [S] violated planes
+
+    unsigned single_planes(unsigned n_sub, unsigned all_planes) const {
+        unsigned m = all_planes;
+        for (unsigned q = 0; q < n_sub; q++)
+            m &= keep[q];
+        return m;
+    }
+};
+
+/// Cells with several planes and few sub-iterations can run the pass-through kernels.
+template <typename F> constexpr bool speculation_capable() {
+    return CellLayout<typename F::Cell>::n_planes >= 2 &&
+           CellLayout<typename F::Cell>::n_planes <= 32 &&
+           F::n_subiterations <= max_spec_subiterations;
+}
+
 template <typename F> struct SweepLauncher {
     using Cell = typename F::Cell;
     using TDV = typename F::TimeDependentValue;
@@ -89,7 +115,8 @@ template <typename F> struct SweepLauncher {
     static void launch(LaunchPlan const &plan, F const &tf, Cell const &halo_value,
                        PlaneSet const &src, PlaneSet const &dst, HaloPush const *push,
                        LaunchRegion const &region, std::size_t iteration0, unsigned n_gens,
-                       TensorMapCache<Cell> &maps_cache, stst_stream_t stream) {
+                       TensorMapCache<Cell> &maps_cache, stst_stream_t stream,
+                       Speculation const *spec = nullptr) {
 #if defined(__CUDACC__)
         constexpr unsigned n_sub = unsigned(F::n_subiterations);
         constexpr unsigned radius = unsigned(F::stencil_radius);
@@ -114,6 +141,20 @@ template <typename F> struct SweepLauncher {
         geo.use_tma = plan.use_tma ? 1u : 0u;
         geo.push = push ? 1u : 0u;
         geo.inv_block_y = (1u << 24) / plan.block_y + 1u;
+        constexpr unsigned all_planes =
+            Layout::n_planes >= 32 ? ~0u : ((1u << Layout::n_planes) - 1u);
+        unsigned single_planes = 0;
+        if (spec) {
+            if constexpr (!speculation_capable<F>())
+                throw std::logic_error("StencilStream-B200: speculation on an incapable functor");
+            for (unsigned q = 0; q < n_sub && q < max_spec_subiterations; q++)
+                geo.keep[q] = spec->probe ? 0u : (spec->keep[q] & all_planes);
+            geo.probe = spec->probe ? 1u : 0u;
+            geo.spec_flags = spec->flags;
+            single_planes = spec->probe ? 0u : spec->single_planes(n_sub, all_planes);
+            if (single_planes != plan.single_planes)
+                throw std::logic_error("StencilStream-B200: plan and speculation masks disagree");
+        }
         geo.iteration0 = iteration0;
         const unsigned out_rows = unsigned(region.out_row_hi - region.out_row_lo);
         const unsigned tiles_y = (out_rows + geo.tile_h - 1) / geo.tile_h;
@@ -126,7 +167,8 @@ template <typename F> struct SweepLauncher {
 
         const unsigned rows = geo.tile_h + 2 * geo.halo;
         const unsigned cols = plan.block_x * unsigned(CW);
-        const std::size_t smem = tile_smem_bytes<Cell>(rows, cols, (n_gens * n_sub > 1) ? 2 : 1);
+        const std::size_t smem =
+            tile_smem_bytes<Cell>(rows, cols, (n_gens * n_sub > 1) ? 2 : 1, single_planes);
 
         static const TensorMapSet no_maps{};
         TensorMapSet const *maps = &no_maps;
@@ -142,23 +184,37 @@ template <typename F> struct SweepLauncher {
                                          std::to_string(region.device));
         }
 
-        auto kernel = fused_sweep_kernel<F, CW, kMode, fixed_block_x<Cell>(), max_threads_per_cta<Cell>(), 1>;
-        static std::size_t configured_smem_per_device[64] = {};
-        std::size_t &configured_smem = configured_smem_per_device[region.device & 63];
-        if (smem > configured_smem) {
-            cudaError_t err = cudaFuncSetAttribute(
-                kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-            if (err != cudaSuccess)
-                throw std::runtime_error(std::string("StencilStream-B200: cannot reserve ") +
-                                         std::to_string(smem) + " bytes of shared memory: " +
-                                         cudaGetErrorString(err));
-            configured_smem = smem;
-        }
-
         const dim3 block(plan.block_x, plan.block_y, 1);
         const dim3 grid(geo.tiles_x * tiles_y, 1, 1);
-        kernel<<<grid, block, smem, static_cast<cudaStream_t>(stream)>>>(
-            tf, halo_value, tdvs, src, dst, push ? *push : no_push, *maps, geo);
+        auto submit = [&](auto kernel, std::size_t &configured_smem) {
+            if (smem > configured_smem) {
+                cudaError_t err = cudaFuncSetAttribute(
+                    kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+                if (err != cudaSuccess)
+                    throw std::runtime_error(std::string("StencilStream-B200: cannot reserve ") +
+                                             std::to_string(smem) + " bytes of shared memory: " +
+                                             cudaGetErrorString(err));
+                configured_smem = smem;
+            }
+            kernel<<<grid, block, smem, static_cast<cudaStream_t>(stream)>>>(
+                tf, halo_value, tdvs, src, dst, push ? *push : no_push, *maps, geo);
+        };
+        static std::size_t configured_smem_per_device[2][64] = {};
+        if constexpr (speculation_capable<F>()) {
+            if (spec) {
+                submit(fused_sweep_kernel<F, CW, kMode, fixed_block_x<Cell>(),
+                                          max_threads_per_cta<Cell>(), 1, true>,
+                       configured_smem_per_device[1][region.device & 63]);
+            } else {
+                submit(fused_sweep_kernel<F, CW, kMode, fixed_block_x<Cell>(),
+                                          max_threads_per_cta<Cell>(), 1, false>,
+                       configured_smem_per_device[0][region.device & 63]);
+            }
+        } else {
+            submit(fused_sweep_kernel<F, CW, kMode, fixed_block_x<Cell>(),
+                                      max_threads_per_cta<Cell>(), 1, false>,
+                   configured_smem_per_device[0][region.device & 63]);
+        }
         cudaError_t err = cudaGetLastError();
         if (err != cudaSuccess)
             throw std::runtime_error(std::string("StencilStream-B200: kernel launch failed: ") +

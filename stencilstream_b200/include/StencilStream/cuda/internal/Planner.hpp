@@ -35,6 +35,7 @@ struct LaunchPlan {
     unsigned halo, hpad;       ///< halo depth of a full launch, and its column-aligned version
     std::size_t smem_bytes;    ///< dynamic shared memory of a full launch
     bool use_tma;
+    unsigned single_planes;    ///< planes the plan assumes are never rewritten (one tile buffer)
 };
 
 inline long env_long(const char *name, long fallback) {
@@ -139,7 +140,7 @@ struct TileShape {
 template <typename Cell>
 TileShape shape_for(unsigned k, unsigned n_sub, unsigned radius, unsigned cw, unsigned col_align,
                     unsigned block_x, unsigned tile_rows_override, std::size_t smem_budget,
-                    unsigned grid_h) {
+                    unsigned grid_h, unsigned single_planes = 0) {
     TileShape s{};
     s.halo = k * n_sub * radius;
     s.hpad = (s.halo + col_align - 1) / col_align * col_align;
@@ -149,7 +150,9 @@ TileShape shape_for(unsigned k, unsigned n_sub, unsigned radius, unsigned cw, un
         return s;
     s.tile_w = s.cols - 2 * s.hpad;
     const unsigned n_buffers = (k * n_sub > 1) ? 2 : 1;
-    const std::size_t per_row = tile_buffer_bytes<Cell>(1, s.cols) * n_buffers;
+    // planes in `single_planes` are never rewritten and live in the first buffer only
+    const std::size_t per_row = tile_buffer_bytes<Cell>(1, s.cols) +
+                                tile_buffer_bytes<Cell>(1, s.cols, single_planes) * (n_buffers - 1);
     // tile_buffer_bytes pads every plane to 128 bytes; leave a little slack for that.
     const std::size_t usable = smem_budget > 4096 ? smem_budget - 2048 : 0;
     unsigned max_rows = unsigned(std::min<std::size_t>(usable / std::max<std::size_t>(per_row, 1), 256));
@@ -161,7 +164,7 @@ TileShape shape_for(unsigned k, unsigned n_sub, unsigned radius, unsigned cw, un
     tile_h = std::min(tile_h, std::max(grid_h, 1u));
     s.tile_h = tile_h;
     s.rows = tile_h + 2 * s.halo;
-    s.smem_bytes = tile_smem_bytes<Cell>(s.rows, s.cols, n_buffers);
+    s.smem_bytes = tile_smem_bytes<Cell>(s.rows, s.cols, n_buffers, single_planes);
     s.efficiency = double(s.tile_h) * s.tile_w / (double(s.rows) * s.cols);
     s.feasible = s.smem_bytes <= smem_budget;
     return s;
@@ -178,7 +181,8 @@ TileShape shape_for(unsigned k, unsigned n_sub, unsigned radius, unsigned cw, un
  */
 template <typename F>
 LaunchPlan make_plan(int device, unsigned grid_h, unsigned grid_w, std::size_t n_iterations,
-                     unsigned fused_override, unsigned tile_rows_override) {
+                     unsigned fused_override, unsigned tile_rows_override,
+                     unsigned single_planes = 0) {
     using Cell = typename F::Cell;
     using L = CellLayout<Cell>;
     constexpr unsigned cw = unsigned(column_group_width<Cell>());
@@ -229,7 +233,7 @@ LaunchPlan make_plan(int device, unsigned grid_h, unsigned grid_w, std::size_t n
 
     auto evaluate = [&](unsigned k, unsigned ctas) {
         return shape_for<Cell>(k, n_sub, radius, cw, col_align, block_x, tile_rows_override,
-                               budget_for(ctas), grid_h);
+                               budget_for(ctas), grid_h, single_planes);
     };
 
     unsigned best_k = 0;
@@ -255,6 +259,8 @@ LaunchPlan make_plan(int device, unsigned grid_h, unsigned grid_w, std::size_t n
         // on-chip work per cell-iteration, fitted to measured sweeps (profiles/r01_sweep_*.log)
         const double onchip = 0.475 * double(sizeof(Cell)) * n_sub + 0.4 * n_sub;
         double best_cost = 0.0;
+        const double launch_overhead_bytes = 10e-6 * 6.5e12;
+        const double grid_cells = std::max(1.0, double(grid_h) * double(grid_w));
         // Candidates: every depth k, with the shared memory of an SM split between `ctas_per_sm`
         // co-resident CTAs (one CTA's staging overlaps the other's sweeps) or given to a single CTA
         // (taller tiles, less halo overhead — what fat cells need). Tiles that waste most of their
@@ -270,7 +276,13 @@ LaunchPlan make_plan(int device, unsigned grid_h, unsigned grid_w, std::size_t n
                     const double solo = (ctas == 1 && ctas_per_sm > 1) ? 1.40 : 1.0;
                     // HBM time and on-chip time overlap only partly: 2-norm instead of max()
                     const double hbm = hbm_bytes / k;
-                    const double cost = solo * std::sqrt(hbm * hbm + onchip * onchip) / s.efficiency;
+                    // Small grids are launch-bound (~10 us per launch measured end to end,
+                    // profiles/r01_s3_driver_hotspot_scaling.cuda.csv): the time of one launch,
+                    // expressed in HBM bytes per cell-iteration, favours deep fusion there and is
+                    // negligible for large grids.
+                    const double launch = launch_overhead_bytes / (grid_cells * k);
+                    const double cost =
+                        solo * std::sqrt(hbm * hbm + onchip * onchip) / s.efficiency + launch;
                     if (best_k == 0 || cost < best_cost * 0.995) {
                         best_k = k;
                         best = s;
@@ -296,6 +308,7 @@ LaunchPlan make_plan(int device, unsigned grid_h, unsigned grid_w, std::size_t n
     plan.hpad = best.hpad;
     plan.smem_bytes = best.smem_bytes;
     plan.use_tma = want_tma && best.cols <= 256 && best.rows <= 256;
+    plan.single_planes = single_planes;
     (void)L::n_planes;
     return plan;
 }

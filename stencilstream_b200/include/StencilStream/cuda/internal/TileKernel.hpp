@@ -79,6 +79,9 @@ inline constexpr int window_shift = 0, window_rotate = 1, window_reload = 2;
 /// Upper bound for the number of iterations fused into one launch (sizes the TDV parameter array).
 inline constexpr unsigned max_fused_iterations = 16;
 
+/// Sub-iterations per iteration up to which speculative plane pass-through is supported.
+inline constexpr unsigned max_spec_subiterations = 4;
+
 /// Geometry of one fused launch; passed by value.
 struct SweepGeometry {
     unsigned grid_h, grid_w; ///< global grid extent (rows, columns)
@@ -93,6 +96,10 @@ struct SweepGeometry {
     unsigned use_tma;        ///< non-zero: stage tiles with TMA box loads (maps valid)
     unsigned push;           ///< non-zero: also store result rows into neighbour slabs (HaloPush valid)
     unsigned inv_block_y;    ///< floor(2^24 / blockDim.y) + 1: row split by multiply-shift, not division
+    // ---- speculative plane pass-through (kernels instantiated with kSpec only; see run_tile) ----
+    unsigned keep[max_spec_subiterations]; ///< per sub-iteration: planes assumed to come out unchanged
+    unsigned probe;          ///< non-zero: record per sub-iteration which planes changed at all
+    unsigned *spec_flags;    ///< device words [0, S): changed per sub-iteration, [S]: violated planes
     unsigned long long iteration0; ///< global index of the first fused iteration
 };
 
@@ -255,23 +262,30 @@ __device__ __forceinline__ void tma_load_2d(void *smem_dst, const void *tensor_m
 /// inside the CTA's dynamic shared memory (what they fetch there is never used for exact cells).
 inline constexpr unsigned tile_guard_bytes = 128;
 
-/// Bytes of one tile buffer (all planes, each plane padded to 128 bytes).
+/// Bytes of one tile buffer (each plane padded to 128 bytes) that holds every plane except those
+/// in `without_planes`.
 template <typename Cell>
-STST_HD inline std::size_t tile_buffer_bytes(unsigned tile_rows, unsigned tile_cols) {
+STST_HD inline std::size_t tile_buffer_bytes(unsigned tile_rows, unsigned tile_cols,
+                                             unsigned without_planes = 0) {
     using L = CellLayout<Cell>;
     std::size_t total = 0;
     for (std::size_t i = 0; i < L::n_planes; i++) {
+        if ((without_planes >> i) & 1u)
+            continue;
         std::size_t b = std::size_t(tile_rows) * tile_cols * L::plane_bytes(i);
         total += (b + 127) / 128 * 128;
     }
     return total;
 }
 
-/// Dynamic shared memory of a CTA: guard, `n_buffers` tile buffers, guard.
+/// Dynamic shared memory of a CTA: guard, `n_buffers` tile buffers, guard. Planes in
+/// `single_planes` (never rewritten, see run_tile) exist in the first buffer only.
 template <typename Cell>
 STST_HD inline std::size_t tile_smem_bytes(unsigned tile_rows, unsigned tile_cols,
-                                           unsigned n_buffers) {
-    return tile_buffer_bytes<Cell>(tile_rows, tile_cols) * n_buffers + 2 * tile_guard_bytes;
+                                           unsigned n_buffers, unsigned single_planes = 0) {
+    return tile_buffer_bytes<Cell>(tile_rows, tile_cols) +
+           tile_buffer_bytes<Cell>(tile_rows, tile_cols, single_planes) * (n_buffers - 1) +
+           2 * tile_guard_bytes;
 }
 
 template <typename Cell> struct TileView {
@@ -290,6 +304,10 @@ template <typename Cell> struct TileView {
             off += (b + 127u) / 128u * 128u;
         }
     }
+
+    /// View whose plane offsets the caller fills in (run_tile with plane pass-through).
+    __device__ __forceinline__ TileView(unsigned char *base, unsigned rows, unsigned cols, int)
+        : base(base), rows(rows), cols(cols) {}
 
     template <std::size_t I> __device__ __forceinline__ typename L::template plane_t<I> *plane() const {
         return reinterpret_cast<typename L::template plane_t<I> *>(base + plane_off[I]);
@@ -401,14 +419,39 @@ __device__ __forceinline__ void stage_tile(TileView<Cell> const &tile, PlaneSet 
  *                               choice for fat cells (tens of bytes), where a resident window of whole
  *                               cells exceeds the register file.
  */
+/// Per-thread bookkeeping of speculative plane pass-through (kSpec kernels).
+struct SpecTrack {
+    unsigned keep;     ///< planes this sweep must not store into the tile (they pass through)
+    unsigned probe;    ///< non-zero: collect `changed`
+    unsigned changed;  ///< planes whose value differed from the centre cell's in this sweep
+    unsigned violated; ///< kept planes whose value differed: the speculation was wrong
+};
+
+/// Bitwise inequality of two plane values.
+template <typename T> __device__ __forceinline__ bool bits_differ(T const &a, T const &b) {
+    if constexpr (sizeof(T) == 1 || sizeof(T) == 2 || sizeof(T) == 4) {
+        return bit_cast_dev<unsigned>(a) != bit_cast_dev<unsigned>(b);
+    } else if constexpr (sizeof(T) == 8) {
+        return bit_cast_dev<unsigned long long>(a) != bit_cast_dev<unsigned long long>(b);
+    } else {
+        const unsigned char *pa = reinterpret_cast<const unsigned char *>(&a);
+        const unsigned char *pb = reinterpret_cast<const unsigned char *>(&b);
+        bool d = false;
+#pragma unroll
+        for (unsigned i = 0; i < sizeof(T); i++)
+            d |= pa[i] != pb[i];
+        return d;
+    }
+}
+
 template <typename F, int CW, bool kInterior, int kMode, int kStore, bool kInLaneMajor,
-          bool kOutLaneMajor, int kTX, std::size_t SUB>
+          bool kOutLaneMajor, int kTX, bool kSpec, std::size_t SUB>
 __device__ __forceinline__ void
 sweep_rows(F const &tf, typename F::Cell const &halo_value,
            typename F::TimeDependentValue const &tdv, std::size_t iteration,
            TileView<typename F::Cell> const &in, TileView<typename F::Cell> const &out,
            bool to_global_arg, PlaneSet const &dst, HaloPush const &push, SweepGeometry const &geo,
-           int gy0, int gx0, int row_lo, int row_hi) {
+           int gy0, int gx0, int row_lo, int row_hi, SpecTrack &spec) {
     using Cell = typename F::Cell;
     using TDV = typename F::TimeDependentValue;
     using L = CellLayout<Cell>;
@@ -533,9 +576,39 @@ sweep_rows(F const &tf, typename F::Cell const &halo_value,
             }
         }
 
+        if constexpr (kSpec) {
+            // Which planes really changed? For a field the functor passes through untouched the
+            // compiler folds the comparison away; for the others it is one compare per cell.
+            for_each_plane<Cell>([&](auto I) {
+                const bool kept = (spec.keep >> I) & 1u;
+                if (kept || spec.probe) {
+                    bool differs = false;
+#pragma unroll
+                    for (int i = 0; i < CW; i++) {
+                        const int gx = gx0 + c0 + i;
+                        bool in_grid = true;
+                        if constexpr (!kInterior)
+                            in_grid = gy >= 0 && gy < int(geo.grid_h) && gx >= 0 && gx < int(geo.grid_w);
+                        if (in_grid)
+                            differs |= bits_differ(L::template get<I>(result[i]),
+                                                   L::template get<I>(win[(top + R) % DW][R + i]));
+                    }
+                    if (differs) {
+                        spec.changed |= 1u << I;
+                        if (kept)
+                            spec.violated |= 1u << I;
+                    }
+                }
+            });
+        }
+
         if (!to_global) {
             for_each_plane<Cell>([&](auto I) {
                 using T = typename L::template plane_t<I>;
+                if constexpr (kSpec) {
+                    if ((spec.keep >> I) & 1u)
+                        return; // passes through: `out` aliases `in` for this plane
+                }
                 if constexpr (kOutLaneMajor) {
                     T *o = out.template plane<I>() + y * cols + tx;
 #pragma unroll
@@ -658,7 +731,7 @@ sweep_rows(F const &tf, typename F::Cell const &halo_value,
 // one tile: stage, run all fused sweeps, write back
 // ------------------------------------------------------------------------------------------------
 
-template <typename F, int CW, bool kInterior, int kMode, int kTX>
+template <typename F, int CW, bool kInterior, int kMode, int kTX, bool kSpec>
 __device__ __forceinline__ void
 run_tile(F const &tf, typename F::Cell const &halo_value,
          TdvArray<typename F::TimeDependentValue> const &tdvs, PlaneSet const &src,
@@ -666,8 +739,10 @@ run_tile(F const &tf, typename F::Cell const &halo_value,
          SweepGeometry const &geo, unsigned char *smem, unsigned long long *mbar, int gy0,
          int gx0) {
     using Cell = typename F::Cell;
+    using L = CellLayout<Cell>;
     constexpr int R = int(F::stencil_radius);
     constexpr unsigned n_sub = unsigned(F::n_subiterations);
+    constexpr unsigned all_planes = (L::n_planes >= 32) ? ~0u : ((1u << L::n_planes) - 1u);
 
     const unsigned rows = geo.tile_h + 2 * geo.halo;
     const unsigned cols = blockDim.x * CW;
@@ -675,6 +750,33 @@ run_tile(F const &tf, typename F::Cell const &halo_value,
 
     TileView<Cell> buf0(smem + tile_guard_bytes, rows, cols);
     TileView<Cell> buf1(smem + tile_guard_bytes + buffer_bytes, rows, cols);
+
+    // Speculative plane pass-through (kSpec). A sweep only stores the planes that are not in its
+    // `keep` mask; a kept plane's current version simply stays where it is. `where` tracks, per
+    // plane, which of the two buffers holds the current version. Planes kept in EVERY sub-iteration
+    // are never rewritten and exist in the first buffer only, so the second buffer is smaller
+    // (more tile rows per CTA). Every kept plane is verified against the functor's result; a
+    // mismatch is reported through geo.spec_flags and the host repeats the update without
+    // speculating on that plane (StencilUpdate.hpp).
+    unsigned single = 0, where = 0;
+    unsigned changed[n_sub] = {};
+    unsigned violated = 0;
+    if constexpr (kSpec) {
+        static_assert(n_sub <= max_spec_subiterations);
+        single = all_planes;
+#pragma unroll
+        for (unsigned q = 0; q < n_sub; q++)
+            single &= geo.keep[q];
+        unsigned off = 0;
+        for_each_plane<Cell>([&](auto I) {
+            if ((single >> I) & 1u) {
+                buf1.plane_off[I] = buf0.plane_off[I] - buffer_bytes; // never addressed
+            } else {
+                buf1.plane_off[I] = off;
+                off += (rows * cols * unsigned(L::plane_bytes(I)) + 127u) / 128u * 128u;
+            }
+        });
+    }
 
     stage_tile<Cell, CW, kInterior>(buf0, src, maps, geo, halo_value, gy0, gx0, mbar);
 
@@ -688,41 +790,62 @@ run_tile(F const &tf, typename F::Cell const &halo_value,
                     const bool last = (g + 1 == geo.n_gens) && (Subs + 1 == n_sub);
                     const int lo = int(step + 1) * R;
                     const int hi = int(rows) - int(step + 1) * R;
-                    TileView<Cell> const &in = (step & 1u) ? buf1 : buf0;
-                    TileView<Cell> const &out = (step & 1u) ? buf0 : buf1;
                     constexpr bool kLM = lane_major_tiles<Cell, CW>() && kMode != window_reload;
                     constexpr std::size_t kSub = Subs;
-                    auto sweep = [&](auto store_c, auto in_lm_c, auto out_lm_c) {
-                        sweep_rows<F, CW, kInterior, kMode, decltype(store_c)::value,
-                                   decltype(in_lm_c)::value, decltype(out_lm_c)::value, kTX, kSub>(
-                            tf, halo_value, tdv, iteration, in, out, last, dst, push, geo, gy0, gx0,
-                            lo, hi);
-                    };
-                    using std::false_type;
-                    using std::true_type;
-                    using grid_c = std::integral_constant<int, store_grid>;
-                    using tile_c = std::integral_constant<int, store_tile>;
-                    using runtime_c = std::integral_constant<int, store_runtime>;
-                    if constexpr (kLM) {
-                        // first sweep reads the TMA-staged (natural) tile, later ones lane-major tiles
-                        if (step == 0) {
+                    SpecTrack track{0u, 0u, 0u, 0u};
+                    auto run = [&](TileView<Cell> const &in, TileView<Cell> const &out) {
+                        auto sweep = [&](auto store_c, auto in_lm_c, auto out_lm_c) {
+                            sweep_rows<F, CW, kInterior, kMode, decltype(store_c)::value,
+                                       decltype(in_lm_c)::value, decltype(out_lm_c)::value, kTX, kSpec,
+                                       kSub>(tf, halo_value, tdv, iteration, in, out, last, dst, push,
+                                             geo, gy0, gx0, lo, hi, track);
+                        };
+                        using std::false_type;
+                        using std::true_type;
+                        using grid_c = std::integral_constant<int, store_grid>;
+                        using tile_c = std::integral_constant<int, store_tile>;
+                        using runtime_c = std::integral_constant<int, store_runtime>;
+                        if constexpr (kLM) {
+                            // first sweep reads the TMA-staged (natural) tile, later ones lane-major
+                            if (step == 0) {
+                                if (last)
+                                    sweep(grid_c{}, false_type{}, false_type{});
+                                else
+                                    sweep(tile_c{}, false_type{}, true_type{});
+                            } else {
+                                if (last)
+                                    sweep(grid_c{}, true_type{}, false_type{});
+                                else
+                                    sweep(tile_c{}, true_type{}, true_type{});
+                            }
+                        } else if constexpr (sizeof(Cell) <= 16) {
                             if (last)
                                 sweep(grid_c{}, false_type{}, false_type{});
                             else
-                                sweep(tile_c{}, false_type{}, true_type{});
+                                sweep(tile_c{}, false_type{}, false_type{});
                         } else {
-                            if (last)
-                                sweep(grid_c{}, true_type{}, false_type{});
-                            else
-                                sweep(tile_c{}, true_type{}, true_type{});
+                            sweep(runtime_c{}, false_type{}, false_type{});
                         }
-                    } else if constexpr (sizeof(Cell) <= 16) {
-                        if (last)
-                            sweep(grid_c{}, false_type{}, false_type{});
-                        else
-                            sweep(tile_c{}, false_type{}, false_type{});
+                    };
+                    if constexpr (kSpec) {
+                        track.keep = geo.keep[kSub] & all_planes;
+                        track.probe = geo.probe;
+                        TileView<Cell> in(smem + tile_guard_bytes, rows, cols, 0);
+                        TileView<Cell> out(smem + tile_guard_bytes, rows, cols, 0);
+                        for_each_plane<Cell>([&](auto I) {
+                            const unsigned a = buf0.plane_off[I];
+                            const unsigned b = buffer_bytes + buf1.plane_off[I];
+                            const bool in_second = (where >> I) & 1u;
+                            in.plane_off[I] = in_second ? b : a;
+                            out.plane_off[I] = ((track.keep >> I) & 1u) ? in.plane_off[I]
+                                                                         : (in_second ? a : b);
+                        });
+                        run(in, out);
+                        where ^= ~track.keep & all_planes;
+                        changed[kSub] |= track.changed;
+                        violated |= track.violated;
                     } else {
-                        sweep(runtime_c{}, false_type{}, false_type{});
+                        run((step & 1u) ? buf1 : buf0, (step & 1u) ? buf0 : buf1);
                     }
                     if (!last)
                         __syncthreads();
@@ -731,6 +854,22 @@ run_tile(F const &tf, typename F::Cell const &halo_value,
                 ...);
         }(std::make_index_sequence<n_sub>{});
     }
+
+    if constexpr (kSpec) {
+        // one atomic per warp and word, and only where there is something to report
+        violated = __reduce_or_sync(0xffffffffu, violated);
+        const bool leader = (threadIdx.x & 31u) == 0;
+        if (violated != 0 && leader)
+            atomicOr(geo.spec_flags + max_spec_subiterations, violated);
+        if (geo.probe) {
+#pragma unroll
+            for (unsigned q = 0; q < n_sub; q++) {
+                const unsigned c = __reduce_or_sync(0xffffffffu, changed[q]);
+                if (c != 0 && leader)
+                    atomicOr(geo.spec_flags + q, c);
+            }
+        }
+    }
 }
 
 /**
@@ -738,7 +877,7 @@ run_tile(F const &tf, typename F::Cell const &halo_value,
  * block: (TWH / CW, row groups), blockDim.x a multiple of 32.
  * Dynamic shared memory: two tile buffers (one if the launch consists of a single sweep).
  */
-template <typename F, int CW, int kMode, int kTX, int kMaxThreads, int kMinBlocks>
+template <typename F, int CW, int kMode, int kTX, int kMaxThreads, int kMinBlocks, bool kSpec = false>
 __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
     fused_sweep_kernel(const __grid_constant__ F tf,
                        const __grid_constant__ typename F::Cell halo_value,
@@ -770,11 +909,11 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
                           tile_gx + int(geo.tile_w + geo.hpad) <= int(geo.grid_w);
 
     if (interior) {
-        run_tile<F, CW, true, kMode, kTX>(tf, halo_value, tdvs, src, dst, push, maps, geo, smem, &mbar,
-                                       gy0, gx0);
+        run_tile<F, CW, true, kMode, kTX, kSpec>(tf, halo_value, tdvs, src, dst, push, maps, geo, smem,
+                                                 &mbar, gy0, gx0);
     } else {
-        run_tile<F, CW, false, (kMode == window_reload ? window_reload : window_shift), kTX>(tf, halo_value, tdvs, src, dst, push, maps, geo, smem, &mbar,
-                                      gy0, gx0);
+        run_tile<F, CW, false, (kMode == window_reload ? window_reload : window_shift), kTX, kSpec>(
+            tf, halo_value, tdvs, src, dst, push, maps, geo, smem, &mbar, gy0, gx0);
     }
 }
 

@@ -161,3 +161,61 @@ def test_tma_and_cp_async_staging_agree(monkeypatch):
         assert update.get_stats().use_tma == int(tma)
         outs.append(got)
     assert outs[0].tobytes() == outs[1].tobytes()
+
+
+# ---- speculative plane pass-through (StencilUpdate::run_speculative, run_tile in TileKernel.hpp) ----
+
+def test_passthrough_planes_are_detected():
+    """HotSpot never changes `power`, FDTD never changes its four material coefficients: after the
+    observing launch the sweeps leave those planes in place (and results stay bit-exact, which every
+    other test in this file checks with the speculation active)."""
+    params, halo, cells = cases.make_case("hotspot", 200, 300, seed=8)
+    _, update = run_gpu("hotspot", params, halo, cells, 0, 12, strict=True)
+    stats = update.get_stats()
+    assert stats.passthrough_planes == 0b10 and stats.speculation_redos == 0
+    params, halo, cells = cases.make_case("fdtd", 120, 130, seed=8)
+    _, update = run_gpu("fdtd", params, halo, cells, 0, 6, strict=True)   # before detect_iteration
+    assert update.get_stats().passthrough_planes & 0b11110000 == 0b11110000
+    # single-plane cells have nothing to pass through
+    params, halo, cells = cases.make_case("jacobi5", 64, 64)
+    _, update = run_gpu("jacobi5", params, halo, cells, 0, 4)
+    assert update.get_stats().passthrough_planes == 0
+
+
+def test_wrong_speculation_is_repeated_without_it(oracle_best):
+    """FDTD's `hz_sum` only starts to change at `detect_iteration` (10 in this case): an updater
+    that observed iterations 0..k-1 believes the plane passes through, a later launch reports the
+    change, and the call is recomputed from the untouched source grid. Results must equal the
+    oracle's bit for bit, for the violating call and for the calls after it."""
+    params, halo, cells = cases.make_case("fdtd", 90, 100, seed=12)
+    want = oracle_best.run("fdtd", params, halo, cells, 0, 30)
+    grid = Grid("fdtd", buffer=cells, strict=True)
+    update = StencilUpdate("fdtd", Params(transition_function=params, halo_value=halo,
+                                          n_iterations=30, blocking=True, fused_iterations=2),
+                           strict=True)
+    out = update(grid)
+    stats = update.get_stats()
+    assert stats.speculation_redos >= 1
+    assert stats.passthrough_planes & 0b1000 == 0          # hz_sum (field 3) is no longer trusted
+    assert stats.passthrough_planes & 0b11110000 == 0b11110000
+    assert out.to_numpy().tobytes() == want.tobytes()
+    assert grid.to_numpy().tobytes() == cells.tobytes()     # the source grid survived the repeat
+    update.get_params().iteration_offset = 30
+    update.get_params().n_iterations = 7
+    again = update(out)
+    want2 = oracle_best.run("fdtd", params, halo, want, 30, 7)
+    assert again.to_numpy().tobytes() == want2.tobytes()
+    assert update.get_stats().speculation_redos == stats.speculation_redos
+
+
+def test_speculation_can_be_switched_off(monkeypatch, oracle_best):
+    """STST_SPECULATE=0 is read once per process, so this only checks that both settings give the
+    oracle's result in whichever mode this process runs; the mode itself is covered by the stats
+    assertions above."""
+    params, halo, cells = cases.make_case("convection_pt", 64, 72, seed=2)
+    want = oracle_best.run("convection_pt", params, halo, cells, 0, 5)
+    got, update = run_gpu("convection_pt", params, halo, cells, 0, 5, strict=True)
+    assert got.tobytes() == want.tobytes()
+    # T is the only field this kernel never writes: 8 of 88 bytes is below the profitability
+    # threshold, so the updater falls back to the unspeculated kernels
+    assert update.get_stats().passthrough_planes == 0
