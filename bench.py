@@ -43,6 +43,12 @@ if str(ROOT) not in sys.path:
 
 WORKLOAD_LABEL = {
     "jacobi5": "Jacobi 5-point fp32 {rows}x{cols}, {iters} generations (BASELINE.json configs[1])",
+    "jacobi_r2": "Jacobi radius-2 star (9-point) fp32 {rows}x{cols}, {iters} generations (BASELINE.json configs[1], "
+                 "radius-2 variant)",
+    "jacobi_r3": "Jacobi radius-3 star (13-point) fp32 {rows}x{cols}, {iters} generations (BASELINE.json configs[1], "
+                 "radius-3 variant)",
+    "conway": "Conway's Game of Life {rows}x{cols}, {iters} generations (BASELINE.json configs[0] rule on a "
+              "bandwidth-sized grid)",
     "hotspot": "Rodinia HotSpot fp32 temp+power {rows}x{cols}, {iters} generations (BASELINE.json configs[2])",
     "fdtd": "FDTD micro-cavity max_grid experiment {rows}x{cols} (coef cells, E/H sub-iterations, tdv source "
             "wave), {iters} time steps (BASELINE.json configs[3])",
@@ -50,9 +56,11 @@ WORKLOAD_LABEL = {
                      "(BASELINE.json configs[4])",
 }
 # (rows per GPU, cols, iterations per step, scaling) used when the command line does not say otherwise
-DEFAULTS = {"jacobi5": (16384, 16384, 1000, "weak"), "hotspot": (16384, 16384, 1000, "weak"),
+DEFAULTS = {"jacobi_r2": (16384, 16384, 1000, "weak"), "jacobi_r3": (16384, 16384, 1000, "weak"),
+            "conway": (16384, 16384, 1000, "weak"),
+            "jacobi5": (16384, 16384, 1000, "weak"), "hotspot": (16384, 16384, 1000, "weak"),
             "fdtd": (4608, 4608, 1000, "strong"), "convection_pt": (4096, 8192, 100, "weak")}
-DTYPE = {"jacobi5": "f32", "hotspot": "f32", "fdtd": "f32", "convection_pt": "f64", "conway": "u8"}
+DTYPE = {"jacobi_r2": "f32", "jacobi_r3": "f32", "jacobi5": "f32", "hotspot": "f32", "fdtd": "f32", "convection_pt": "f64", "conway": "u8"}
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -65,6 +73,17 @@ def make_workload(name: str, rows: int, cols: int):
 
     if name == "jacobi5":
         return W.jacobi5_params(), 0.0, lambda view, r0, r1, total: fill_jacobi(view, r0, r1, total, cols)
+    if name in ("jacobi_r2", "jacobi_r3"):
+        return W.jacobi_star_params(int(name[-1])), 0.0, \
+            lambda view, r0, r1, total: fill_jacobi(view, r0, r1, total, cols)
+    if name == "conway":
+        from stencilstream_b200 import _native
+
+        def fill_conway(view, r0, r1, total):
+            for lo in range(r0, r1, 1024):  # seeded per row band: slabs generate their own rows
+                hi = min(lo + 1024, r1)
+                view[lo - r0:hi - r0] = W.conway_soup(hi - lo, cols, seed=42 + lo)
+        return _native.ConwayParams(), None, fill_conway
     if name == "hotspot":
         return W.hotspot_params(rows, cols), (0.0, 0.0), \
             lambda view, r0, r1, total: fill_hotspot(view, r0, r1, total, cols)

@@ -87,6 +87,10 @@ template <typename Cell> constexpr int max_threads_per_cta() {
     if (sizeof(Cell) <= 8)
         return STST_LIGHT_MAX_THREADS;
 #endif
+#if defined(STST_MID_MAX_THREADS)
+    if (sizeof(Cell) > 16 && sizeof(Cell) <= 64)
+        return STST_MID_MAX_THREADS;
+#endif
     return (sizeof(Cell) > 64 && column_group_width<Cell>() == 1) ? 512 : 256;
 }
 
@@ -259,8 +263,6 @@ LaunchPlan make_plan(int device, unsigned grid_h, unsigned grid_w, std::size_t n
         // on-chip work per cell-iteration, fitted to measured sweeps (profiles/r01_sweep_*.log)
         const double onchip = 0.475 * double(sizeof(Cell)) * n_sub + 0.4 * n_sub;
         double best_cost = 0.0;
-        const double launch_overhead_bytes = 10e-6 * 6.5e12;
-        const double grid_cells = std::max(1.0, double(grid_h) * double(grid_w));
         // Candidates: every depth k, with the shared memory of an SM split between `ctas_per_sm`
         // co-resident CTAs (one CTA's staging overlaps the other's sweeps) or given to a single CTA
         // (taller tiles, less halo overhead — what fat cells need). Tiles that waste most of their
@@ -276,13 +278,12 @@ LaunchPlan make_plan(int device, unsigned grid_h, unsigned grid_w, std::size_t n
                     const double solo = (ctas == 1 && ctas_per_sm > 1) ? 1.40 : 1.0;
                     // HBM time and on-chip time overlap only partly: 2-norm instead of max()
                     const double hbm = hbm_bytes / k;
-                    // Small grids are launch-bound (~10 us per launch measured end to end,
-                    // profiles/r01_s3_driver_hotspot_scaling.cuda.csv): the time of one launch,
-                    // expressed in HBM bytes per cell-iteration, favours deep fusion there and is
-                    // negligible for large grids.
-                    const double launch = launch_overhead_bytes / (grid_cells * k);
-                    const double cost =
-                        solo * std::sqrt(hbm * hbm + onchip * onchip) / s.efficiency + launch;
+                    // (A launch-overhead term that pushes small grids towards deep fusion was
+                    // tried and made them slower — 1024^2 HotSpot 249 -> 162 GCell-updates/s: a
+                    // launch over a grid of one wave of CTAs lasts as long as ONE CTA's load ->
+                    // k sweeps -> store sequence, which grows with k;
+                    // profiles/r01_s3_driver_hotspot_scaling_deepfusion.csv.)
+                    const double cost = solo * std::sqrt(hbm * hbm + onchip * onchip) / s.efficiency;
                     if (best_k == 0 || cost < best_cost * 0.995) {
                         best_k = k;
                         best = s;
@@ -296,6 +297,27 @@ LaunchPlan make_plan(int device, unsigned grid_h, unsigned grid_w, std::size_t n
         if (best_k == 0)
             throw std::invalid_argument(
                 "StencilStream-B200: cell type too large for a shared-memory tile");
+    }
+
+    // Small grids: with fewer CTAs than the GPU holds at once, a launch lasts as long as ONE CTA's
+    // load -> sweeps -> store sequence, however few SMs take part. Shorter tiles spread the grid over
+    // just under one resident set of CTAs (a second, mostly empty wave costs more than it gains:
+    // 1024^2 HotSpot, 29-row tiles 166, 13-row tiles 205, 19-row tiles — 270 CTAs on 296 slots —
+    // 249 GCell-updates/s; Jacobi 340 -> 408; 2048^2 and larger are unaffected;
+    // profiles/r01_s3_sweep_small_grids.log). Not below twice the halo (tile efficiency).
+    if (tile_rows_override == 0 && best.tile_h > 2 * best.halo) {
+        const unsigned tiles_x = (std::max(grid_w, 1u) + best.tile_w - 1) / best.tile_w;
+        const unsigned slots = unsigned(std::max(info.sm_count, 1)) * ctas_per_sm;
+        const unsigned want_tile_rows = std::max(1u, slots * 95u / 100u / tiles_x);
+        const unsigned tile_h =
+            std::max(2 * best.halo, (std::max(grid_h, 1u) + want_tile_rows - 1) / want_tile_rows);
+        if (tile_h < best.tile_h) {
+            const TileShape shrunk =
+                shape_for<Cell>(best_k, n_sub, radius, cw, col_align, block_x, tile_h,
+                                budget_for(ctas_per_sm), grid_h, single_planes);
+            if (shrunk.feasible)
+                best = shrunk;
+        }
     }
 
     LaunchPlan plan{};
