@@ -256,6 +256,7 @@ typedef struct stst_slab_info {
     int device;
     unsigned fused_iterations, tile_h, tile_w, block_x, block_y, use_tma, overlap;
     size_t smem_bytes;
+    unsigned passthrough_planes; /* planes the sweeps currently leave in place (see below) */
 } stst_slab_info;
 
 /* fused_iterations: upper bound for k (0 = automatic); all slabs of a grid must end up with the same
@@ -290,6 +291,20 @@ int stst_slab_copy_field_rows_to_host(stst_slab *slab, size_t field, size_t firs
                                       void *values, size_t bytes);
 /* Uses transition_function, halo_value, iteration_offset, n_iterations and blocking of `params`. */
 int stst_slab_update(stst_slab *slab, const stst_update_params *params);
+/*
+ * Speculative plane pass-through on slabs (the single-grid updater does all of this by itself, see
+ * stst_update_stats.passthrough_planes). Fields the transition function never changes are left in
+ * place by the tile sweeps; every pass verifies that. A slab has no untouched source grid to repeat
+ * from, and its neighbours consume the rows it pushes, so the owner of the slabs drives the repeat:
+ *   enable_speculation(1) once;  per update:  backup -> update -> take_violations on EVERY slab ->
+ *   OR the masks together (across processes: an all-reduce) -> if non-zero: drop_passthrough(mask),
+ *   restore and update again on every slab.
+ */
+int stst_slab_enable_speculation(stst_slab *slab, int enable, int *enabled /* may be NULL */);
+int stst_slab_backup(stst_slab *slab);
+int stst_slab_restore(stst_slab *slab);
+int stst_slab_take_violations(stst_slab *slab, unsigned *planes);
+int stst_slab_drop_passthrough(stst_slab *slab, unsigned planes);
 int stst_slab_synchronize(stst_slab *slab);
 /* The stream a CUDA event must be recorded on to bracket the slab's work (after join). */
 int stst_slab_record_event(stst_slab *slab, void *event);

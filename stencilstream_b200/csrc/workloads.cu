@@ -183,6 +183,11 @@ struct SlabBase {
     virtual void update(const stst_update_params &p) = 0;
     virtual void synchronize() = 0;
     virtual void record(void *event) = 0;
+    virtual bool enable_speculation(bool on) = 0;
+    virtual void backup() = 0;
+    virtual void restore() = 0;
+    virtual unsigned take_violations() = 0;
+    virtual void drop_passthrough(unsigned planes) = 0;
 };
 
 template <typename F, typename ParamBlock> struct SlabHolder final : SlabBase {
@@ -221,6 +226,7 @@ template <typename F, typename ParamBlock> struct SlabHolder final : SlabBase {
         out.use_tma = plan.use_tma ? 1u : 0u;
         out.overlap = cfg.overlap ? 1u : 0u;
         out.smem_bytes = plan.smem_bytes;
+        out.passthrough_planes = slab->passthrough_planes();
     }
     void *device_base() override { return slab->device_base(); }
     int device() const override { return slab->get_config().device; }
@@ -260,6 +266,11 @@ template <typename F, typename ParamBlock> struct SlabHolder final : SlabBase {
     }
     void synchronize() override { slab->synchronize(); }
     void record(void *event) override { slab->record(event); }
+    bool enable_speculation(bool on) override { return slab->enable_speculation(on); }
+    void backup() override { slab->backup(); }
+    void restore() override { slab->restore(); }
+    unsigned take_violations() override { return slab->take_violations(); }
+    void drop_passthrough(unsigned planes) override { slab->drop_passthrough(planes); }
 };
 
 struct WorkloadEntry {
@@ -714,6 +725,53 @@ STST_EXPORT int stst_slab_update(stst_slab *slab, const stst_update_params *para
         return report(STST_ERR_INVALID_ARGUMENT, "null argument");
     return guarded([&] {
         slab->impl->update(*params);
+        return STST_OK;
+    });
+}
+
+STST_EXPORT int stst_slab_enable_speculation(stst_slab *slab, int enable, int *enabled) {
+    if (!slab)
+        return report(STST_ERR_INVALID_ARGUMENT, "null argument");
+    return guarded([&] {
+        const bool on = slab->impl->enable_speculation(enable != 0);
+        if (enabled)
+            *enabled = on ? 1 : 0;
+        return STST_OK;
+    });
+}
+
+STST_EXPORT int stst_slab_backup(stst_slab *slab) {
+    if (!slab)
+        return report(STST_ERR_INVALID_ARGUMENT, "null argument");
+    return guarded([&] {
+        slab->impl->backup();
+        return STST_OK;
+    });
+}
+
+STST_EXPORT int stst_slab_restore(stst_slab *slab) {
+    if (!slab)
+        return report(STST_ERR_INVALID_ARGUMENT, "null argument");
+    return guarded([&] {
+        slab->impl->restore();
+        return STST_OK;
+    });
+}
+
+STST_EXPORT int stst_slab_take_violations(stst_slab *slab, unsigned *planes) {
+    if (!slab || !planes)
+        return report(STST_ERR_INVALID_ARGUMENT, "null argument");
+    return guarded([&] {
+        *planes = slab->impl->take_violations();
+        return STST_OK;
+    });
+}
+
+STST_EXPORT int stst_slab_drop_passthrough(stst_slab *slab, unsigned planes) {
+    if (!slab)
+        return report(STST_ERR_INVALID_ARGUMENT, "null argument");
+    return guarded([&] {
+        slab->impl->drop_passthrough(planes);
         return STST_OK;
     });
 }

@@ -170,9 +170,96 @@ template <typename F> class SlabUpdate {
     ~SlabUpdate() {
         (void)stst_stream_synchronize(interior_stream);
         (void)stst_stream_synchronize(boundary_stream);
+        device_free(cfg.device, spec_flags, interior_stream);
+        device_free(cfg.device, backup_block, interior_stream);
+        (void)stst_stream_synchronize(interior_stream);
         (void)stst_stream_destroy(interior_stream);
         (void)stst_stream_destroy(boundary_stream);
         (void)stst_free_ipc(cfg.device, base);
+    }
+
+    // ---- speculative plane pass-through on slabs ---------------------------------------------------
+    //
+    // Same mechanism as StencilUpdate::run_speculative (see there and run_tile in TileKernel.hpp): the
+    // first pass observes which planes the transition function leaves unchanged, later passes leave
+    // those planes in place, every pass verifies them. What differs is the repeat after a wrong
+    // guess: a slab has no untouched source grid, and its neighbours have already consumed the rows it
+    // pushed. The owner of the slabs therefore (1) calls backup() before run(), (2) combines
+    // take_violations() of ALL slabs after it, and (3) if any slab reports one, has every slab
+    // drop_passthrough(mask), restore() and run() again (sharding.py does this with one all-reduce
+    // per call). Off unless enable_speculation(true).
+
+    /// Turn pass-through on or off for the following run() calls (no-op for functors without a
+    /// second plane). Returns whether it is on.
+    bool enable_speculation(bool on) {
+        if constexpr (speculation_capable<F>())
+            spec_enabled = on && env_long("STST_SPECULATE", 1) != 0;
+        return spec_enabled;
+    }
+    bool speculation_active() const { return spec_enabled && !spec_exhausted(); }
+
+    /// Planes that currently pass through every sub-iteration.
+    unsigned passthrough_planes() const {
+        if (!spec_enabled || !spec_probed)
+            return 0;
+        return current_spec().single_planes(n_sub, all_planes);
+    }
+
+    /// Save the current generation (owned and ghost rows) so that restore() can return to it.
+    void backup() {
+        join_streams();
+        // the ghost rows of the current generation are complete once the neighbours have raised
+        // this epoch's flags — the same condition a pass waits for
+        for (int s = 0; s < 2; s++) {
+            if (has_side(s))
+                STST_RT_CHECK(stst_stream_wait_value32_geq(interior_stream, my_flag(s),
+                                                           unsigned(epoch + 1)));
+        }
+        const std::size_t bytes = plane_set_bytes();
+        if (!backup_block)
+            backup_block = device_alloc(cfg.device, bytes, interior_stream);
+        STST_RT_CHECK(stst_memcpy_d2d_async(backup_block, plane_set_begin(int(epoch & 1)), bytes,
+                                            interior_stream));
+        fork_streams();
+    }
+
+    /// Return to the generation saved by backup(), as the *current* buffer. Every slab of the grid
+    /// must do this at the same point (their ghost rows are part of what is restored).
+    void restore() {
+        if (!backup_block)
+            throw std::logic_error("StencilStream-B200: restore() without backup()");
+        join_streams();
+        STST_RT_CHECK(stst_memcpy_d2d_async(plane_set_begin(int(epoch & 1)), backup_block,
+                                            plane_set_bytes(), interior_stream));
+        fork_streams();
+    }
+
+    /// Planes for which some pass since the last call saw a kept plane change. Waits for the slab.
+    unsigned take_violations() {
+        if (!spec_flags)
+            return 0;
+        join_streams();
+        unsigned *host = static_cast<unsigned *>(pinned_alloc(flag_bytes));
+        unsigned violated = 0;
+        try {
+            STST_RT_CHECK(stst_memcpy_d2h_async(host, spec_flags, flag_bytes, interior_stream));
+            STST_RT_CHECK(stst_stream_synchronize(interior_stream));
+            violated = host[max_spec_subiterations];
+            STST_RT_CHECK(stst_memset_async(spec_flags, 0, flag_bytes, interior_stream));
+        } catch (...) {
+            pinned_free(host);
+            throw;
+        }
+        pinned_free(host);
+        fork_streams();
+        return violated;
+    }
+
+    /// Never let `planes` pass through again.
+    void drop_passthrough(unsigned planes) {
+        for (unsigned q = 0; q < n_sub; q++)
+            spec_keep[q] &= ~planes;
+        settle_speculation();
     }
 
     // ---- topology ---------------------------------------------------------------------------------
@@ -305,7 +392,20 @@ template <typename F> class SlabUpdate {
         std::size_t remaining = n_iterations;
         while (remaining > 0) {
             const unsigned n_gens = unsigned(std::min(remaining, k));
-            pass(tf, halo_value, iteration, n_gens);
+            if (spec_enabled && !spec_probed) {
+                // the first pass ever observes; its result tells which planes may stay in place
+                ensure_spec_flags();
+                Speculation observe{};
+                observe.probe = true;
+                observe.flags = spec_flags;
+                pass(tf, halo_value, iteration, n_gens, &observe);
+                read_observation();
+            } else if (speculation_active()) {
+                const Speculation spec = current_spec();
+                pass(tf, halo_value, iteration, n_gens, &spec);
+            } else {
+                pass(tf, halo_value, iteration, n_gens, nullptr);
+            }
             iteration += n_gens;
             remaining -= n_gens;
         }
@@ -369,7 +469,86 @@ template <typename F> class SlabUpdate {
 
     void fork_streams() { join_streams(); }
 
-    void pass(F const &tf, Cell const &halo_value, std::size_t iteration0, unsigned n_gens) {
+    static constexpr unsigned n_sub = unsigned(F::n_subiterations);
+    static constexpr unsigned all_planes =
+        Layout::n_planes >= 32 ? ~0u : ((1u << Layout::n_planes) - 1u);
+    static constexpr std::size_t flag_bytes = sizeof(unsigned) * (max_spec_subiterations + 1);
+
+    Speculation current_spec() const {
+        Speculation spec{};
+        for (unsigned q = 0; q < n_sub && q < max_spec_subiterations; q++)
+            spec.keep[q] = spec_keep[q];
+        spec.flags = spec_flags;
+        return spec;
+    }
+
+    bool spec_exhausted() const {
+        if (!spec_probed)
+            return false;
+        for (unsigned q = 0; q < n_sub && q < max_spec_subiterations; q++)
+            if (spec_keep[q] != 0)
+                return false;
+        return true;
+    }
+
+    void ensure_spec_flags() {
+        if (spec_flags)
+            return;
+        spec_flags = static_cast<unsigned *>(device_alloc(cfg.device, flag_bytes, interior_stream));
+        STST_RT_CHECK(stst_memset_async(spec_flags, 0, flag_bytes, interior_stream));
+        join_streams();
+    }
+
+    /// After the observing pass: keep what never changed, if that is worth it (same rule as
+    /// StencilUpdate::drop_unprofitable_speculation), and plan the tiles for it. The fusion depth
+    /// stays what the slab was built with — it fixes the ghost rows.
+    void read_observation() {
+        join_streams();
+        unsigned *host = static_cast<unsigned *>(pinned_alloc(flag_bytes));
+        try {
+            STST_RT_CHECK(stst_memcpy_d2h_async(host, spec_flags, flag_bytes, interior_stream));
+            STST_RT_CHECK(stst_stream_synchronize(interior_stream));
+            for (unsigned q = 0; q < n_sub && q < max_spec_subiterations; q++)
+                spec_keep[q] = ~host[q] & all_planes;
+            STST_RT_CHECK(stst_memset_async(spec_flags, 0, flag_bytes, interior_stream));
+        } catch (...) {
+            pinned_free(host);
+            throw;
+        }
+        pinned_free(host);
+        spec_probed = true;
+        settle_speculation();
+        fork_streams();
+    }
+
+    void settle_speculation() {
+        unsigned single = current_spec().single_planes(n_sub, all_planes);
+        std::size_t bytes = 0;
+        for (std::size_t i = 0; i < Layout::n_planes; i++)
+            if ((single >> i) & 1u)
+                bytes += Layout::plane_bytes(i);
+        if (4 * bytes < sizeof(Cell)) {
+            for (unsigned q = 0; q < max_spec_subiterations; q++)
+                spec_keep[q] = 0;
+            single = 0;
+        }
+        spec_plan = make_plan<F>(cfg.device, unsigned(cfg.row_hi - cfg.row_lo),
+                                 unsigned(cfg.grid_cols), max_fused_iterations,
+                                 plan.fused_iterations, cfg.tile_rows, single);
+        if (spec_plan.fused_iterations != plan.fused_iterations)
+            throw std::logic_error("StencilStream-B200: pass-through changed the fusion depth");
+    }
+
+    std::size_t plane_set_bytes() const {
+        return layout.plane_offset[1][0] - layout.plane_offset[0][0];
+    }
+    unsigned char *plane_set_begin(int buffer) const {
+        return static_cast<unsigned char *>(base) + layout.plane_offset[buffer][0];
+    }
+
+    void pass(F const &tf, Cell const &halo_value, std::size_t iteration0, unsigned n_gens,
+              Speculation const *spec) {
+        const LaunchPlan &use_plan = (spec && !spec->probe) ? spec_plan : plan;
         const int cur = int(epoch & 1);
         const PlaneSet src = layout.planes(base, cur);
         const PlaneSet dst = layout.planes(base, cur ^ 1);
@@ -417,9 +596,9 @@ template <typename F> class SlabUpdate {
             region.out_row_lo = int(lo);
             region.out_row_hi = int(hi);
             region.tile_h = strip ? unsigned(hi - lo) : 0;
-            SweepLauncher<F>::launch(plan, tf, halo_value, src, dst,
+            SweepLauncher<F>::launch(use_plan, tf, halo_value, src, dst,
                                      (with_push && pushes) ? &push : nullptr, region, iteration0,
-                                     n_gens, tensor_maps, stream);
+                                     n_gens, tensor_maps, stream, spec);
             n_launches++;
         };
 
@@ -512,6 +691,12 @@ template <typename F> class SlabUpdate {
     std::size_t peer_row_lo[2], peer_row_hi[2];
     TensorMapCache<Cell> tensor_maps;
     std::unique_ptr<Event> boundary_done, interior_done;
+    // speculative plane pass-through
+    bool spec_enabled = false, spec_probed = false;
+    unsigned spec_keep[max_spec_subiterations] = {};
+    unsigned *spec_flags = nullptr;
+    LaunchPlan spec_plan{};
+    void *backup_block = nullptr;
 };
 
 } // namespace internal

@@ -41,7 +41,7 @@ class SlabInfo(C.Structure):
         ("n_launches", C.c_size_t), ("epoch", C.c_size_t), ("device", C.c_int),
         ("fused_iterations", C.c_uint), ("tile_h", C.c_uint), ("tile_w", C.c_uint),
         ("block_x", C.c_uint), ("block_y", C.c_uint), ("use_tma", C.c_uint), ("overlap", C.c_uint),
-        ("smem_bytes", C.c_size_t),
+        ("smem_bytes", C.c_size_t), ("passthrough_planes", C.c_uint),
     ]
 
 
@@ -64,6 +64,11 @@ def _slab_lib(strict: bool | None = None):
         lib.stst_slab_update.argtypes = [vp, C.POINTER(_native.UpdateParams)]
         lib.stst_slab_synchronize.argtypes = [vp]
         lib.stst_slab_record_event.argtypes = [vp, vp]
+        lib.stst_slab_enable_speculation.argtypes = [vp, C.c_int, C.POINTER(C.c_int)]
+        lib.stst_slab_backup.argtypes = [vp]
+        lib.stst_slab_restore.argtypes = [vp]
+        lib.stst_slab_take_violations.argtypes = [vp, C.POINTER(C.c_uint)]
+        lib.stst_slab_drop_passthrough.argtypes = [vp, C.c_uint]
         lib.stst_slab_max_abs.argtypes = [vp, C.POINTER(_native.FieldExtent), C.c_size_t,
                                           C.POINTER(C.c_double)]
         lib.stst_slab_copy_field_rows_to_host.argtypes = [vp, C.c_size_t, C.c_size_t, C.c_size_t, vp,
@@ -160,6 +165,27 @@ class NativeSlab:
     def update(self, native_params) -> None:
         _check(self._lib, self._lib.stst_slab_update(self._handle, C.byref(native_params)))
 
+    # -- speculative plane pass-through (include/stst_workloads.h) ------------------------------------
+    def enable_speculation(self, on: bool = True) -> bool:
+        enabled = C.c_int(0)
+        _check(self._lib, self._lib.stst_slab_enable_speculation(self._handle, int(on),
+                                                                 C.byref(enabled)))
+        return bool(enabled.value)
+
+    def backup(self) -> None:
+        _check(self._lib, self._lib.stst_slab_backup(self._handle))
+
+    def restore(self) -> None:
+        _check(self._lib, self._lib.stst_slab_restore(self._handle))
+
+    def take_violations(self) -> int:
+        planes = C.c_uint(0)
+        _check(self._lib, self._lib.stst_slab_take_violations(self._handle, C.byref(planes)))
+        return int(planes.value)
+
+    def drop_passthrough(self, planes: int) -> None:
+        _check(self._lib, self._lib.stst_slab_drop_passthrough(self._handle, int(planes)))
+
     def synchronize(self) -> None:
         _check(self._lib, self._lib.stst_slab_synchronize(self._handle))
 
@@ -179,7 +205,7 @@ class ShardedStencilUpdate:
 
     def __init__(self, workload: str, params: Params, grid_rows: int, grid_cols: int, *, rank: int,
                  world: int, device: int = 0, comm: Any = None, overlap: bool = True,
-                 strict: bool | None = None,
+                 strict: bool | None = None, speculate: bool = True,
                  slab_factory: Callable[..., Any] | None = None):
         if world > 1 and comm is None:
             raise ValueError("a process group is needed to exchange slab handles")
@@ -215,6 +241,17 @@ class ShardedStencilUpdate:
                     handle, lo, hi, _ = everyone[other]
                     self.slab.attach_ipc(side, handle, lo, hi)
         self._keepalive = None
+        # plane pass-through: every slab must agree on whether the protocol runs at all
+        wants = bool(speculate) and hasattr(self.slab, "enable_speculation") and \
+            self.slab.enable_speculation(True)
+        if world > 1:
+            votes = [None] * world
+            comm.all_gather_object(votes, wants)
+            wants = all(votes)
+            if not wants and hasattr(self.slab, "enable_speculation"):
+                self.slab.enable_speculation(False)
+        self.speculating = wants
+        self.n_speculation_redos = 0
 
     # -- data ---------------------------------------------------------------------------------------
     @property
@@ -291,9 +328,33 @@ class ShardedStencilUpdate:
 
     def __call__(self) -> "ShardedStencilUpdate":
         """Advance the slab by `params.n_iterations` iterations starting at `params.iteration_offset`
-        (asynchronous unless `params.blocking`). Collective."""
-        self.slab.update(self._native_params())
-        return self
+        (asynchronous unless `params.blocking` — or unless plane pass-through is active, whose
+        verification ends every call with one all-reduce). Collective."""
+        if not self.speculating:
+            self.slab.update(self._native_params())
+            return self
+        # Speculative plane pass-through: the sweeps leave fields the transition function never
+        # changes in place and verify that in every pass. If ANY slab saw such a field change, all
+        # slabs return to the saved generation and repeat the call without trusting that field.
+        self.slab.backup()
+        while True:
+            self.slab.update(self._native_params())
+            violated = self._combine_or(self.slab.take_violations())
+            if violated == 0:
+                return self
+            self.n_speculation_redos += 1
+            self.slab.drop_passthrough(violated)
+            self.slab.restore()
+
+    def _combine_or(self, mask: int) -> int:
+        if self.world == 1:
+            return mask
+        import torch
+        device = "cuda" if self._comm.get_backend() == "nccl" else "cpu"
+        # NCCL has no bitwise OR: one 0/1 entry per plane, combined with MAX
+        bits = torch.tensor([(mask >> i) & 1 for i in range(32)], dtype=torch.int32, device=device)
+        self._comm.all_reduce(bits, op=self._comm.ReduceOp.MAX)
+        return sum(int(b) << i for i, b in enumerate(bits.cpu().tolist()))
 
     def synchronize(self) -> None:
         self.slab.synchronize()

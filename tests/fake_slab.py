@@ -91,6 +91,32 @@ class HostSlab:
             iteration += n_gens
             remaining -= n_gens
 
+    # plane pass-through: the host double copies whole cells; it takes part in the protocol (so that
+    # ShardedStencilUpdate's backup / verify / repeat sequence runs under gloo) and can be told to
+    # report a violation once, to exercise the repeat
+    inject_violation_once = 0
+
+    def enable_speculation(self, on=True):
+        self.speculation = bool(on)
+        return self.speculation
+
+    def backup(self):
+        self._saved = (self.cells.copy(), {k: (None if v is None else v.copy())
+                                           for k, v in self.ghost_rows.items()})
+        self.log.append("backup")
+
+    def restore(self):
+        self.cells = self._saved[0].copy()
+        self.ghost_rows = {k: (None if v is None else v.copy()) for k, v in self._saved[1].items()}
+        self.log.append("restore")
+
+    def take_violations(self):
+        mask, self.inject_violation_once = self.inject_violation_once, 0
+        return mask
+
+    def drop_passthrough(self, planes):
+        self.log.append(("drop", planes))
+
     def synchronize(self):
         pass
 

@@ -59,21 +59,33 @@ def _worker(rank, world, port, workload, shape, offset, n, depth, failures, mode
         params, halo, cells = cases_mod.make_case(workload, *shape, seed=21)
         if "kat" in workload:
             cells = cases_mod.kat_input(*shape, offset)
-        if mode == "host":
+        if mode in ("host", "host_violation"):
             extra = dict(slab_factory=lambda **kw: HostSlab(checker, depth, **kw))
         else:  # the real thing: sm_100a kernels, -fmad=false build, IPC-mapped neighbours
             from stencilstream_b200 import _native
             import ctypes as C
             count = C.c_int(0)
             _native.runtime_lib().stst_device_count(C.byref(count))
-            extra = dict(device=rank % max(count.value, 1), strict=True, overlap=(mode == "cuda"))
+            extra = dict(device=rank % max(count.value, 1), strict=True,
+                         overlap=(mode != "cuda-no-overlap"))
         update = ShardedStencilUpdate(
             workload, Params(transition_function=params, halo_value=halo, iteration_offset=offset,
                              n_iterations=n, blocking=True, fused_iterations=depth),
             shape[0], shape[1], rank=rank, world=world, comm=dist, **extra)
         lo, hi = update.row_lo, update.row_hi
         update.load(cells[lo:hi])
+        if mode == "host_violation" and rank == world - 1:
+            update.slab.inject_violation_once = 0b10     # one slab reports a changed plane once
         update()
+        if mode == "cuda-redo_expected":
+            if update.n_speculation_redos < 1:
+                failures.put(f"rank {rank}: no repeat although hz_sum changes at iteration 10")
+            if update.info().passthrough_planes & 0b11111000 != 0b11110000:
+                failures.put(f"rank {rank}: pass-through planes {update.info().passthrough_planes:#b}")
+        if mode == "host_violation":
+            # every slab went back to the saved generation and repeated the call
+            if update.n_speculation_redos != 1 or update.slab.log.count("restore") != 1:
+                failures.put(f"rank {rank}: redos {update.n_speculation_redos}, log {update.slab.log}")
         # a second call resumes where the first stopped (iteration_offset is a live parameter)
         update.get_params().iteration_offset += n
         update.get_params().n_iterations = 2
@@ -105,6 +117,10 @@ def _worker(rank, world, port, workload, shape, offset, n, depth, failures, mode
                                   != want.view(np.uint8).reshape(shape[0], -1))
                 failures.put(f"{workload}: sharded result differs from the whole-grid oracle, "
                              f"first at row {bad[0][0]}")
+            if mode == "host_violation":
+                dist.barrier()
+                dist.destroy_process_group()
+                return
             if mode != "host":
                 if update.info().fused_iterations != depth:
                     failures.put(f"{workload}: fusion depth {update.info().fused_iterations}")
@@ -140,6 +156,12 @@ def _worker(rank, world, port, workload, shape, offset, n, depth, failures, mode
 ])
 def test_sharded_update_equals_whole_grid(world, workload, shape, offset, n, depth, built):
     run_group(world, workload, shape, offset, n, depth, "host")
+
+
+def test_reported_violation_makes_every_slab_repeat_the_call(built):
+    """Plane pass-through on slabs: one slab reporting a violation makes ALL slabs restore the saved
+    generation and repeat (one all-reduce per call); the result is still the whole-grid oracle's."""
+    run_group(3, "hotspot", (45, 37), 0, 7, 3, "host_violation")
 
 
 def run_group(world, workload, shape, offset, n, depth, mode):

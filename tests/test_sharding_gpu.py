@@ -25,3 +25,12 @@ pytestmark = pytest.mark.gpu
 ])
 def test_sharded_update_equals_whole_grid_on_gpu(mode, world, workload, shape, offset, n, depth, built):
     run_group(world, workload, shape, offset, n, depth, mode)
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_wrong_passthrough_guess_is_repeated_on_every_slab(world, built):
+    """FDTD's `hz_sum` starts to change at detect_iteration = 10: the slabs' observing pass (iterations
+    0-1) marks it as passing through, a later pass reports the change, all slabs restore the saved
+    generation and repeat the call. `redo_expected` makes the workers assert that this happened and
+    that the material coefficients still pass through afterwards."""
+    run_group(world, "fdtd", (150, 333), 0, 14, 2, "cuda-redo_expected")
