@@ -434,7 +434,10 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     stats = update.get_stats() if runner is None else runner.info()
     k = int(stats.fused_iterations)
     plan = {"tile": [int(stats.tile_h), int(stats.tile_w)], "block": [int(stats.block_x), int(stats.block_y)],
-            "tma": bool(stats.use_tma), "smem_bytes": int(stats.smem_bytes)}
+            "tma": bool(stats.use_tma), "smem_bytes": int(stats.smem_bytes),
+            "passthrough_planes": int(stats.passthrough_planes),
+            "speculation_redos": int(stats.speculation_redos if runner is None
+                                     else runner.n_speculation_redos)}
 
     # ---- roofline of the fused sweep kernel -----------------------------------------------------------
     peak, peak_source = measured_peak_gbs()

@@ -208,7 +208,7 @@ template <typename F, typename ParamBlock> struct SlabHolder final : SlabBase {
     void info(stst_slab_info &out) override {
         std::memset(&out, 0, sizeof(out));
         auto const &cfg = slab->get_config();
-        auto const &plan = slab->get_plan();
+        auto const &plan = slab->get_active_plan();
         out.grid_rows = cfg.grid_rows;
         out.grid_cols = cfg.grid_cols;
         out.row_lo = cfg.row_lo;

@@ -325,7 +325,10 @@ template <concepts::TransitionFunction F, bool split_cell_structure = false> cla
         for (std::size_t i = 0; i < Layout::n_planes; i++)
             if ((single >> i) & 1u)
                 bytes += Layout::plane_bytes(i);
-        if (4 * bytes < sizeof(Cell)) {
+        // ... and cells beyond 64 bytes run at the register limit of their 512-thread CTAs: the
+        // per-plane buffer bookkeeping spills there (convection: 9.2 -> 8.2 GCell-updates/s even
+        // with four of eleven fields constant in the benchmark input)
+        if (4 * bytes < sizeof(Cell) || sizeof(Cell) > 64) {
             for (unsigned q = 0; q < n_sub; q++)
                 spec_keep[q] = 0;
         }

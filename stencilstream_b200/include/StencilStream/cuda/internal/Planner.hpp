@@ -242,26 +242,35 @@ LaunchPlan make_plan(int device, unsigned grid_h, unsigned grid_w, std::size_t n
 
     unsigned best_k = 0;
     TileShape best{};
+    // Cost model in "HBM-byte equivalents" per cell-iteration.
+    const double hbm_bytes = 2.0 * double(sizeof(Cell)) * n_sub; // one read + one write / sweep
+    // on-chip work per cell-iteration, fitted to measured sweeps (profiles/r01_sweep_*.log)
+    const double onchip = 0.475 * double(sizeof(Cell)) * n_sub + 0.4 * n_sub;
     if (fused_override > 0) {
         // `fused_iterations` is an upper bound: take the deepest fusion not exceeding it whose tile
-        // still fits into shared memory.
+        // still fits into shared memory — split between `ctas_per_sm` CTAs or given to one,
+        // whichever the cost model prefers (a feasible but tiny tile must not win by default:
+        // FDTD with pass-through fits k = 3 into half an SM's shared memory with 1-row tiles).
         for (unsigned k = std::min(fused_override, k_cap); k >= 1 && best_k == 0; k--) {
-            TileShape s = evaluate(k, ctas_per_sm);
-            if (!s.feasible)
-                s = evaluate(k, 1);
-            if (s.feasible) {
-                best_k = k;
-                best = s;
+            double best_cost = 0.0;
+            for (unsigned ctas : {ctas_per_sm, 1u}) {
+                const TileShape s = evaluate(k, ctas);
+                if (!s.feasible)
+                    continue;
+                const double solo = (ctas == 1 && ctas_per_sm > 1) ? 1.40 : 1.0;
+                const double hbm = hbm_bytes / k;
+                const double cost = solo * std::sqrt(hbm * hbm + onchip * onchip) / s.efficiency;
+                if (best_k == 0 || cost < best_cost) {
+                    best_k = k;
+                    best = s;
+                    best_cost = cost;
+                }
             }
         }
         if (best_k == 0)
             throw std::invalid_argument(
                 "StencilStream-B200: cell type too large for a shared-memory tile");
     } else {
-        // Cost model in "HBM-byte equivalents" per cell-iteration.
-        const double hbm_bytes = 2.0 * double(sizeof(Cell)) * n_sub; // one read + one write / sweep
-        // on-chip work per cell-iteration, fitted to measured sweeps (profiles/r01_sweep_*.log)
-        const double onchip = 0.475 * double(sizeof(Cell)) * n_sub + 0.4 * n_sub;
         double best_cost = 0.0;
         // Candidates: every depth k, with the shared memory of an SM split between `ctas_per_sm`
         // co-resident CTAs (one CTA's staging overlaps the other's sweeps) or given to a single CTA

@@ -273,6 +273,10 @@ template <typename F> class SlabUpdate {
     bool has_up() const { return cfg.row_lo > 0; }
     bool has_down() const { return cfg.row_hi < cfg.grid_rows; }
     LaunchPlan const &get_plan() const { return plan; }
+    /// The plan the next pass will use (taller tiles once planes pass through).
+    LaunchPlan const &get_active_plan() const {
+        return (spec_enabled && spec_probed && !spec_exhausted()) ? spec_plan : plan;
+    }
     Config const &get_config() const { return cfg; }
     std::size_t get_n_launches() const { return n_launches; }
     std::size_t get_epoch() const { return epoch; }
@@ -527,7 +531,10 @@ template <typename F> class SlabUpdate {
         for (std::size_t i = 0; i < Layout::n_planes; i++)
             if ((single >> i) & 1u)
                 bytes += Layout::plane_bytes(i);
-        if (4 * bytes < sizeof(Cell)) {
+        // ... and cells beyond 64 bytes run at the register limit of their 512-thread CTAs: the
+        // per-plane buffer bookkeeping spills there (convection: 9.2 -> 8.2 GCell-updates/s even
+        // with four of eleven fields constant in the benchmark input)
+        if (4 * bytes < sizeof(Cell) || sizeof(Cell) > 64) {
             for (unsigned q = 0; q < max_spec_subiterations; q++)
                 spec_keep[q] = 0;
             single = 0;
