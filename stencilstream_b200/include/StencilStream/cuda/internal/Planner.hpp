@@ -74,6 +74,10 @@ template <typename Cell> constexpr int column_group_width() {
         return 1;
     if (widest >= 8)
         return 2;
+#if defined(STST_BYTE_COLUMN_GROUP_WIDTH)
+    if (sizeof(Cell) == 1)
+        return STST_BYTE_COLUMN_GROUP_WIDTH;
+#endif
 #if defined(STST_LIGHT_COLUMN_GROUP_WIDTH)
     if (CellLayout<Cell>::n_planes == 1 && widest == 4)
         return STST_LIGHT_COLUMN_GROUP_WIDTH;
