@@ -282,6 +282,11 @@ int stst_slab_copy_rows_from_host(stst_slab *slab, size_t first_row, size_t n_ro
                                   const void *cells, size_t bytes);
 int stst_slab_copy_rows_to_host(stst_slab *slab, size_t first_row, size_t n_rows, void *cells,
                                 size_t bytes);
+/* Replace the owned rows by those of `source`: a slab of the same grid, row range and cell type on
+ * the same device, usually the slab of ANOTHER workload over the same cells (convection alternates
+ * "convection_pt" and "convection_thermal" updates). Device-to-device; waits for `source`; else
+ * STST_ERR_RANGE. Follow it with stst_slab_exchange_halos. */
+int stst_slab_copy_from_slab(stst_slab *slab, stst_slab *source);
 int stst_slab_exchange_halos(stst_slab *slab);
 /* As stst_grid_max_abs, extents in GLOBAL grid coordinates; out[q] covers the rows this slab owns
  * (-inf if none): combine the slabs' results with max (across processes: an all-reduce). */

@@ -186,7 +186,7 @@ WORKLOADS_SYMBOLS = [
     "stst_grid_make_similar", "stst_grid_destroy", "stst_grid_shape", "stst_grid_copy_from_host",
     "stst_grid_copy_to_host", "stst_grid_sync_to_device", "stst_grid_host_accessor", "stst_grid_host_image_is_pinned",
     "stst_grid_max_abs", "stst_grid_copy_field_to_host", "stst_grid_copy_field_from_host",
-    "stst_slab_max_abs", "stst_slab_copy_field_rows_to_host", "stst_slab_enable_speculation",
+    "stst_slab_max_abs", "stst_slab_copy_field_rows_to_host", "stst_slab_copy_from_slab", "stst_slab_enable_speculation",
     "stst_slab_backup", "stst_slab_restore", "stst_slab_take_violations", "stst_slab_drop_passthrough",
     "stst_update_create",
     "stst_update_set_params", "stst_update_apply", "stst_update_get_stats", "stst_update_destroy",

@@ -24,6 +24,7 @@ from typing import Callable
 import numpy as np
 
 from .api import Grid, Params, StencilUpdate
+from .sharding import ShardedStencilUpdate
 from . import workloads as W
 
 
@@ -87,6 +88,62 @@ def run_convection(config: dict, *, cells: np.ndarray | None = None, strict: boo
         if on_frame is not None and it % nout == 0:
             on_frame(it, grid.field_to_numpy("T")[:nx, :ny])
     return grid, steps
+
+
+def run_convection_sharded(config: dict, *, rank: int, world: int, comm=None, device: int = 0,
+                           strict: bool | None = None, fused_iterations: int = 0,
+                           slab_factory=None,
+                           on_frame: Callable[[int, int, int, np.ndarray], None] | None = None):
+    """`run_convection` on a row-sharded grid, one process per GPU (collective: every process of the
+    group calls it with the same `config`).
+
+    The pseudo-transient and the thermal update are two transition functions over the same cells, i.e.
+    two slab objects per GPU; the cells move between them device to device (`load_from`). The five
+    max-norms of a convergence check are reduced per slab on its GPU and combined with one
+    all-reduce(MAX) — the only collective in the loop. `on_frame(it, row_lo, row_hi, T_rows)` receives
+    this rank's rows of the temperature field every `nout` steps. Returns (the pseudo-transient
+    ShardedStencilUpdate holding the final cells, [ConvectionStep, ...])."""
+    exp = W.ConvectionExperiment(config)
+    nx, ny = exp.nx, exp.ny
+    rows, cols = exp.grid_shape
+    iter_max, nt = int(config["iterMax"]), int(config["nt"])
+    nout, nerr, epsilon = int(config["nout"]), int(config["nerr"]), float(config["epsilon"])
+    common = dict(rank=rank, world=world, device=device, comm=comm, strict=strict,
+                  slab_factory=slab_factory)
+    pseudo_transient = ShardedStencilUpdate(
+        "convection_pt", Params(transition_function=exp.pseudo_transient_params(), halo_value=None,
+                                n_iterations=nerr, blocking=True,
+                                fused_iterations=fused_iterations), rows, cols, **common)
+    thermal = ShardedStencilUpdate(
+        "convection_thermal", Params(transition_function=exp.thermal_params(0.0), halo_value=None,
+                                     n_iterations=1, blocking=True), rows, cols, **common)
+    lo, hi = pseudo_transient.row_lo, pseudo_transient.row_hi
+    pseudo_transient.load(exp.initial_grid(lo, hi))
+    extents = convection_norm_extents(nx, ny)
+    steps = []
+    for it in range(1, nt + 1):
+        errV = errP = 2 * epsilon
+        norms = dict.fromkeys((e[0] for e in extents), float("-inf"))
+        iterations = 0
+        while iterations < iter_max and (errV > epsilon or errP > epsilon):
+            pseudo_transient()
+            norms = dict(zip((e[0] for e in extents), pseudo_transient.max_abs(extents)))
+            errV = norms["ErrV"] / (1e-12 + norms["Vy"])
+            errP = norms["ErrP"] / (1e-12 + norms["Pt"])
+            iterations += nerr
+        with np.errstate(divide="ignore"):
+            dt_adv = min(np.float64(exp.dx) / norms["Vx"], np.float64(exp.dy) / norms["Vy"]) / 2.1
+        dt = float(min(exp.dt_diff, dt_adv))
+        thermal.get_params().transition_function = exp.thermal_params(dt)
+        thermal.load_from(pseudo_transient)
+        thermal()
+        pseudo_transient.load_from(thermal)
+        steps.append(ConvectionStep(it, iterations, errV, errP, dt, norms))
+        if on_frame is not None and it % nout == 0:
+            T = pseudo_transient.field_to_numpy("T")
+            on_frame(it, lo, hi, T[:max(0, min(hi, nx) - lo), :ny])
+    thermal.close()
+    return pseudo_transient, steps
 
 
 def run_fdtd(config: dict, *, n_timesteps: int | None = None, n_snap_timesteps: int | None = None,

@@ -183,6 +183,9 @@ struct SlabBase {
     virtual void update(const stst_update_params &p) = 0;
     virtual void synchronize() = 0;
     virtual void record(void *event) = 0;
+    virtual void copy_from(SlabBase &other) = 0;
+    virtual sc::internal::PlaneSet current_planes() = 0;
+    virtual std::size_t ghost() const = 0;
     virtual bool enable_speculation(bool on) = 0;
     virtual void backup() = 0;
     virtual void restore() = 0;
@@ -266,6 +269,21 @@ template <typename F, typename ParamBlock> struct SlabHolder final : SlabBase {
     }
     void synchronize() override { slab->synchronize(); }
     void record(void *event) override { slab->record(event); }
+    sc::internal::PlaneSet current_planes() override { return slab->current_planes(); }
+    std::size_t ghost() const override { return slab->ghost_rows(); }
+    void copy_from(SlabBase &other) override {
+        stst_slab_info mine, theirs;
+        info(mine);
+        other.info(theirs);
+        if (other.cell_bytes() != cell_bytes() || theirs.grid_rows != mine.grid_rows ||
+            theirs.grid_cols != mine.grid_cols || theirs.row_lo != mine.row_lo ||
+            theirs.row_hi != mine.row_hi)
+            throw std::range_error("The source slab has not the same rows, columns or cell type");
+        if (other.device() != device())
+            throw std::invalid_argument("the two slabs live on different devices");
+        other.synchronize(); // its current generation must be complete before it is read
+        slab->copy_owned_rows_from(other.current_planes(), other.ghost());
+    }
     bool enable_speculation(bool on) override { return slab->enable_speculation(on); }
     void backup() override { slab->backup(); }
     void restore() override { slab->restore(); }
@@ -725,6 +743,15 @@ STST_EXPORT int stst_slab_update(stst_slab *slab, const stst_update_params *para
         return report(STST_ERR_INVALID_ARGUMENT, "null argument");
     return guarded([&] {
         slab->impl->update(*params);
+        return STST_OK;
+    });
+}
+
+STST_EXPORT int stst_slab_copy_from_slab(stst_slab *slab, stst_slab *source) {
+    if (!slab || !source)
+        return report(STST_ERR_INVALID_ARGUMENT, "null argument");
+    return guarded([&] {
+        slab->impl->copy_from(*source->impl);
         return STST_OK;
     });
 }

@@ -355,6 +355,31 @@ template <typename F> class SlabUpdate {
         STST_RT_CHECK(stst_stream_synchronize(interior_stream));
     }
 
+    /// The planes that hold the current generation, and how many ghost rows precede the owned rows
+    /// in them (for copy_owned_rows_from of another slab).
+    PlaneSet current_planes() const { return layout.planes(base, int(epoch & 1)); }
+
+    /**
+     * Replace the owned rows by those of another slab of the SAME grid rows, columns and cell type
+     * on the same device — typically the slab of a different transition function over the same
+     * cells (mantle convection alternates a pseudo-transient and a thermal update,
+     * reference examples/convection/convection.cpp:405-455). Device-to-device, one copy per plane;
+     * follow it with exchange_halos(). `other_*` describe the source slab's current planes, whose
+     * contents must be complete (the caller synchronises the source slab first).
+     */
+    void copy_owned_rows_from(PlaneSet const &other_planes, std::size_t other_ghost) {
+        join_streams();
+        const PlaneSet mine = current_planes();
+        for (std::size_t i = 0; i < Layout::n_planes; i++) {
+            const std::size_t row_bytes = layout.pitch[i] * Layout::plane_bytes(i);
+            STST_RT_CHECK(stst_memcpy_d2d_async(
+                static_cast<unsigned char *>(mine.base[i]) + ghost * row_bytes,
+                static_cast<const unsigned char *>(other_planes.base[i]) + other_ghost * row_bytes,
+                owned_rows() * row_bytes, interior_stream));
+        }
+        fork_streams();
+    }
+
     /// Publish the owned boundary rows of the current buffer to the neighbours' ghost rows (needed
     /// once after upload(); afterwards every pass pushes its own boundary rows). Collective: every
     /// slab of the grid has to call it at the same point of its sequence of operations.

@@ -64,6 +64,7 @@ def _slab_lib(strict: bool | None = None):
         lib.stst_slab_update.argtypes = [vp, C.POINTER(_native.UpdateParams)]
         lib.stst_slab_synchronize.argtypes = [vp]
         lib.stst_slab_record_event.argtypes = [vp, vp]
+        lib.stst_slab_copy_from_slab.argtypes = [vp, vp]
         lib.stst_slab_enable_speculation.argtypes = [vp, C.c_int, C.POINTER(C.c_int)]
         lib.stst_slab_backup.argtypes = [vp]
         lib.stst_slab_restore.argtypes = [vp]
@@ -144,6 +145,11 @@ class NativeSlab:
 
     def exchange_halos(self) -> None:
         _check(self._lib, self._lib.stst_slab_exchange_halos(self._handle))
+
+    def copy_from_slab(self, source: "NativeSlab") -> None:
+        """Replace the owned rows by those of `source` (same grid, rows and cell type, same device;
+        device-to-device)."""
+        _check(self._lib, self._lib.stst_slab_copy_from_slab(self._handle, source._handle))
 
     def max_abs(self, extents) -> list[float]:
         """[(field, rows, cols), ...] in GLOBAL grid coordinates -> this slab's share of each
@@ -273,6 +279,17 @@ class ShardedStencilUpdate:
         for lo in range(self.row_lo, self.row_hi, chunk_rows):
             hi = min(lo + chunk_rows, self.row_hi)
             self.slab.copy_rows_from_host(lo - self.row_lo, generate(lo, hi))
+        self.slab.exchange_halos()
+
+    def load_from(self, other: "ShardedStencilUpdate") -> None:
+        """`load()` from the slab of another updater over the same grid and cell type (e.g. the
+        pseudo-transient and the thermal update of mantle convection): the owned rows move device to
+        device, then the boundary rows are published. Collective."""
+        if (other.grid_rows, other.grid_cols, other.row_lo, other.row_hi) != \
+                (self.grid_rows, self.grid_cols, self.row_lo, self.row_hi):
+            from .api import RangeError
+            raise RangeError("The source slab has not the same rows and columns")
+        self.slab.copy_from_slab(other.slab)
         self.slab.exchange_halos()
 
     def to_numpy(self, out: np.ndarray | None = None) -> np.ndarray:

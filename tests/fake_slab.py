@@ -58,6 +58,11 @@ class HostSlab:
     def copy_to_host(self, out):
         out[...] = self.cells
 
+    def copy_from_slab(self, source):
+        assert source.cells.shape == self.cells.shape and source.dtype == self.dtype
+        self.cells = source.cells.copy()
+        self.log.append("copy_from_slab")
+
     def max_abs(self, extents):
         out = []
         for field, rows, cols in extents:

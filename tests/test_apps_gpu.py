@@ -7,35 +7,10 @@ import numpy as np
 import pytest
 
 from stencilstream_b200 import workloads as W
-from stencilstream_b200.apps import convection_norm_extents, run_convection, run_fdtd
+from cases import oracle_convection
+from stencilstream_b200.apps import run_convection, run_fdtd
 
 pytestmark = pytest.mark.gpu
-
-
-def oracle_convection(oracle, config):
-    exp = W.ConvectionExperiment(config)
-    nx, ny = exp.nx, exp.ny
-    cells = exp.initial_grid()
-    steps, frames = [], []
-    for it in range(1, int(config["nt"]) + 1):
-        errV = errP = 2 * config["epsilon"]
-        iterations = 0
-        while iterations < config["iterMax"] and (errV > config["epsilon"] or errP > config["epsilon"]):
-            cells = oracle.run("convection_pt", exp.pseudo_transient_params(), None, cells, 0,
-                               config["nerr"])
-            norms = {f: float(np.abs(cells[f][:r, :c]).max())
-                     for f, r, c in convection_norm_extents(nx, ny)}
-            errV = norms["ErrV"] / (1e-12 + norms["Vy"])
-            errP = norms["ErrP"] / (1e-12 + norms["Pt"])
-            iterations += config["nerr"]
-        with np.errstate(divide="ignore"):
-            dt = float(min(exp.dt_diff, min(np.float64(exp.dx) / norms["Vx"],
-                                            np.float64(exp.dy) / norms["Vy"]) / 2.1))
-        cells = oracle.run("convection_thermal", exp.thermal_params(dt), None, cells, 0, 1)
-        steps.append((it, iterations, errV, errP, dt))
-        if it % config["nout"] == 0:
-            frames.append((it, cells["T"][:nx, :ny].copy()))
-    return cells, steps, frames
 
 
 def test_convection_application_loop_matches_oracle(oracle_best):
