@@ -192,7 +192,9 @@ template <typename F> class SlabUpdate {
     /// Turn pass-through on or off for the following run() calls (no-op for functors without a
     /// second plane). Returns whether it is on.
     bool enable_speculation(bool on) {
-        if constexpr (speculation_capable<F>())
+        // (cells beyond 64 bytes never profit, see settle_speculation: do not even start the
+        // protocol for them — its backup would be a third copy of a very large slab)
+        if constexpr (speculation_capable<F>() && sizeof(Cell) <= 64)
             spec_enabled = on && env_long("STST_SPECULATE", 1) != 0;
         return spec_enabled;
     }

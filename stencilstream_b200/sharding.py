@@ -356,22 +356,29 @@ class ShardedStencilUpdate:
         self.slab.backup()
         while True:
             self.slab.update(self._native_params())
-            violated = self._combine_or(self.slab.take_violations())
+            still_useful = int(self.slab.info().passthrough_planes) != 0
+            violated, anyone_useful = self._combine_or(self.slab.take_violations(), still_useful)
             if violated == 0:
+                # once no slab has a plane left to pass through, the protocol (backup, all-reduce)
+                # is dropped for good — on every rank at the same call, the decision is collective
+                self.speculating = anyone_useful
                 return self
             self.n_speculation_redos += 1
             self.slab.drop_passthrough(violated)
             self.slab.restore()
 
-    def _combine_or(self, mask: int) -> int:
+    def _combine_or(self, mask: int, flag: bool) -> tuple[int, bool]:
+        """(bitwise OR of `mask`, logical OR of `flag`) over all ranks."""
         if self.world == 1:
-            return mask
+            return mask, flag
         import torch
         device = "cuda" if self._comm.get_backend() == "nccl" else "cpu"
-        # NCCL has no bitwise OR: one 0/1 entry per plane, combined with MAX
-        bits = torch.tensor([(mask >> i) & 1 for i in range(32)], dtype=torch.int32, device=device)
+        # NCCL has no bitwise OR: one 0/1 entry per plane (and one for the flag), combined with MAX
+        bits = torch.tensor([(mask >> i) & 1 for i in range(32)] + [int(flag)], dtype=torch.int32,
+                            device=device)
         self._comm.all_reduce(bits, op=self._comm.ReduceOp.MAX)
-        return sum(int(b) << i for i, b in enumerate(bits.cpu().tolist()))
+        values = bits.cpu().tolist()
+        return sum(int(b) << i for i, b in enumerate(values[:32])), bool(values[32])
 
     def synchronize(self) -> None:
         self.slab.synchronize()

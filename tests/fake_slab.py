@@ -39,7 +39,8 @@ class HostSlab:
     # ---- interface of NativeSlab -----------------------------------------------------------------
     def info(self):
         return SimpleNamespace(fused_iterations=self.k, ghost_rows=self.ghost, row_lo=self.row_lo,
-                               row_hi=self.row_hi, n_launches=self.n_launches)
+                               row_hi=self.row_hi, n_launches=self.n_launches,
+                               passthrough_planes=1 if getattr(self, "speculation", False) else 0)
 
     def ipc_handle(self) -> bytes:
         return pickle.dumps(dist.get_rank()).ljust(64, b"\0")
