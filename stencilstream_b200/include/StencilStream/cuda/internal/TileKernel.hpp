@@ -143,6 +143,39 @@ inline constexpr bool is_shuffleable_v = std::is_trivially_copyable_v<T> &&
                                          (sizeof(T) == 1 || sizeof(T) == 2 || sizeof(T) == 4 ||
                                           sizeof(T) == 8);
 
+// ---- shared-memory accounting (host and device; used by the planner) ---------------------------
+
+/// Unused bytes in front of the first and behind the last tile buffer: edge-column loads of the
+/// first/last thread of a tile row reach up to `radius` elements beyond their row, and must stay
+/// inside the CTA's dynamic shared memory (what they fetch there is never used for exact cells).
+inline constexpr unsigned tile_guard_bytes = 128;
+
+/// Bytes of one tile buffer (each plane padded to 128 bytes) that holds every plane except those
+/// in `without_planes`.
+template <typename Cell>
+STST_HD inline std::size_t tile_buffer_bytes(unsigned tile_rows, unsigned tile_cols,
+                                             unsigned without_planes = 0) {
+    using L = CellLayout<Cell>;
+    std::size_t total = 0;
+    for (std::size_t i = 0; i < L::n_planes; i++) {
+        if ((without_planes >> i) & 1u)
+            continue;
+        std::size_t b = std::size_t(tile_rows) * tile_cols * L::plane_bytes(i);
+        total += (b + 127) / 128 * 128;
+    }
+    return total;
+}
+
+/// Dynamic shared memory of a CTA: guard, `n_buffers` tile buffers, guard. Planes in
+/// `single_planes` (never rewritten, see run_tile) exist in the first buffer only.
+template <typename Cell>
+STST_HD inline std::size_t tile_smem_bytes(unsigned tile_rows, unsigned tile_cols,
+                                           unsigned n_buffers, unsigned single_planes = 0) {
+    return tile_buffer_bytes<Cell>(tile_rows, tile_cols) +
+           tile_buffer_bytes<Cell>(tile_rows, tile_cols, single_planes) * (n_buffers - 1) +
+           2 * tile_guard_bytes;
+}
+
 #if defined(__CUDACC__)
 
 template <typename To, typename From> __device__ __forceinline__ To bit_cast_dev(From const &f) {
@@ -256,37 +289,6 @@ __device__ __forceinline__ void tma_load_2d(void *smem_dst, const void *tensor_m
 // ------------------------------------------------------------------------------------------------
 // shared-memory tile bookkeeping
 // ------------------------------------------------------------------------------------------------
-
-/// Unused bytes in front of the first and behind the last tile buffer: edge-column loads of the
-/// first/last thread of a tile row reach up to `radius` elements beyond their row, and must stay
-/// inside the CTA's dynamic shared memory (what they fetch there is never used for exact cells).
-inline constexpr unsigned tile_guard_bytes = 128;
-
-/// Bytes of one tile buffer (each plane padded to 128 bytes) that holds every plane except those
-/// in `without_planes`.
-template <typename Cell>
-STST_HD inline std::size_t tile_buffer_bytes(unsigned tile_rows, unsigned tile_cols,
-                                             unsigned without_planes = 0) {
-    using L = CellLayout<Cell>;
-    std::size_t total = 0;
-    for (std::size_t i = 0; i < L::n_planes; i++) {
-        if ((without_planes >> i) & 1u)
-            continue;
-        std::size_t b = std::size_t(tile_rows) * tile_cols * L::plane_bytes(i);
-        total += (b + 127) / 128 * 128;
-    }
-    return total;
-}
-
-/// Dynamic shared memory of a CTA: guard, `n_buffers` tile buffers, guard. Planes in
-/// `single_planes` (never rewritten, see run_tile) exist in the first buffer only.
-template <typename Cell>
-STST_HD inline std::size_t tile_smem_bytes(unsigned tile_rows, unsigned tile_cols,
-                                           unsigned n_buffers, unsigned single_planes = 0) {
-    return tile_buffer_bytes<Cell>(tile_rows, tile_cols) +
-           tile_buffer_bytes<Cell>(tile_rows, tile_cols, single_planes) * (n_buffers - 1) +
-           2 * tile_guard_bytes;
-}
 
 template <typename Cell> struct TileView {
     using L = CellLayout<Cell>;
