@@ -2,7 +2,8 @@
 """Benchmark of the StencilStream-B200 generation loop.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--workload jacobi5|hotspot] [--rows R --cols C --iterations I]
+                    [--workload jacobi5|jacobi_r2|jacobi_r3|hotspot|fdtd|convection_pt|conway]
+                    [--rows R --cols C --iterations I]
 
 Metric (BASELINE.json / reference scripts/benchmark-common.jl:97-98): GCell-updates/s =
 rows * cols * n_iterations / time, one "update" being one full iteration (all sub-iterations).
