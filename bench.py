@@ -246,10 +246,11 @@ def time_cpu_oracle(workload: str, rows: int, cols: int, target_seconds: float =
     cells = np.empty((sample_rows, cols), dtype=dtype)
     fill(cells, 0, sample_rows, sample_rows)
 
+    impl.run(workload, params, halo, cells, 0, 1)   # first touch, thread start-up
     t0 = time.perf_counter()
-    impl.run(workload, params, halo, cells, 0, 1)
-    per_iter = time.perf_counter() - t0
-    iters = int(max(2, min(200, target_seconds / max(per_iter, 1e-3))))
+    impl.run(workload, params, halo, cells, 0, 3)
+    per_iter = (time.perf_counter() - t0) / 3
+    iters = int(max(2, min(2000, target_seconds / max(per_iter, 1e-4))))
     t0 = time.perf_counter()
     impl.run(workload, params, halo, cells, 0, iters)
     elapsed = time.perf_counter() - t0
@@ -305,6 +306,29 @@ def measured_peak_gbs():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def measured_dram_traffic(workload: str, rows: int, cols: int, k: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the fused sweep kernel from the
+    committed `ncu --set full` capture of this workload (profiles/r01_s3_ncu_<workload>*_summary.txt),
+    or None if there is no capture of this configuration (captures are of the default grid sizes with
+    the planner's fusion depth)."""
+    captured = {"jacobi5": ("r01_s3_ncu_jacobi5_k6_summary.txt", 16384, 16384, 6),
+                "hotspot": ("r01_s3_ncu_hotspot_passthrough_summary.txt", 16384, 16384, 4),
+                "convection_pt": ("r01_s3_ncu_convection_pt_summary.txt", 4096, 8192, 1)}
+    if workload not in captured:
+        return None, None
+    name, c_rows, c_cols, c_k = captured[workload]
+    path = ROOT / "profiles" / name
+    if (rows, cols, k) != (c_rows, c_cols, c_k) or not path.exists():
+        return None, None
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    total = 0.0
+    for line in path.read_text().splitlines():
+        parts = line.split()
+        if len(parts) == 3 and parts[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            total += float(parts[1]) * scale.get(parts[2], 1.0)
+    return (total or None), f"profiles/{name}"
 
 
 def run_ours(args, rank: int, world: int, local_rank: int):
@@ -448,9 +472,11 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     bytes_per_launch = info.bytes_per_cell_iteration * rows * cols * iters / launches_per_step
     launch_ms = ms_per_step / launches_per_step
     achieved = bytes_per_launch / (launch_ms * 1e-3) / 1e9
+    traffic, traffic_source = measured_dram_traffic(workload, rows, cols, k)
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-        "traffic": None, "peak_source": peak_source,
+        "traffic": traffic, "traffic_source": traffic_source,
+        "algorithmic_bytes_per_launch": bytes_per_launch, "peak_source": peak_source,
         "kernel": "fused_sweep_kernel", "fused_iterations": k,
         "algorithmic_bytes_per_cell_iteration": int(info.bytes_per_cell_iteration),
         "note": "effective fraction: k fused iterations cross HBM once, so it may exceed the physical "
