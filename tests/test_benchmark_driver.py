@@ -32,3 +32,47 @@ def test_model_runtime_is_bandwidth_or_launch_bound():
 
 def test_operation_counts_are_the_reference_drivers():
     assert driver.OPERATIONS_PER_CELL == {"jacobi5": 9, "hotspot": 15, "fdtd": 24, "convection_pt": 67}
+
+
+# ---- bench.py host logic (no GPU) -------------------------------------------------------------------
+
+def _bench():
+    spec2 = importlib.util.spec_from_file_location("stst_bench", ROOT / "bench.py")
+    mod = importlib.util.module_from_spec(spec2)
+    spec2.loader.exec_module(mod)
+    return mod
+
+
+def test_bench_inputs_are_the_reference_recipes_and_slab_wise_generation_agrees():
+    """bench.py fills slabs row range by row range; stitched together they must be the whole-grid
+    inputs of stencilstream_b200.workloads (which restate the reference's generators)."""
+    import numpy as np
+    from stencilstream_b200 import _native
+    from stencilstream_b200 import workloads as W
+    bench = _bench()
+    rows, cols = 96, 80
+    for workload, whole in (("jacobi5", W.jacobi_input(rows, cols)),
+                            ("jacobi_r2", W.jacobi_input(rows, cols)),
+                            ("hotspot", W.hotspot_input(rows, cols))):
+        _, _, fill = bench.make_workload(workload, rows, cols)
+        stitched = np.zeros((rows, cols), dtype=_native.CELL_DTYPES[workload])
+        for lo, hi in ((0, 31), (31, 64), (64, 96)):
+            fill(stitched[lo:hi], lo, hi, rows)
+        assert stitched.tobytes() == whole.tobytes(), workload
+    exp = W.ConvectionExperiment(W.convection_benchmark_config(res=64, n_iters=1, lx=1.5, ly=1.0))
+    _, _, fill = bench.make_workload("convection_pt", *exp.grid_shape)
+    stitched = np.zeros(exp.grid_shape, dtype=_native.CELL_DTYPES["convection_pt"])
+    fill(stitched[:40], 0, 40, exp.grid_shape[0])
+    fill(stitched[40:], 40, exp.grid_shape[0], exp.grid_shape[0])
+    assert stitched.tobytes() == exp.initial_grid().tobytes()
+
+
+def test_bench_roofline_traffic_comes_from_the_committed_capture():
+    bench = _bench()
+    traffic, source = bench.measured_dram_traffic("jacobi5", 16384, 16384, 6)
+    assert source and (ROOT / source).exists()
+    # one read and one write of a 1 GiB grid per launch, within 5 % (halo re-reads hit L2; the last
+    # dirty lines are still in L2 when the kernel ends)
+    assert abs(traffic / (2 * 2 ** 30) - 1.0) < 0.05
+    assert bench.measured_dram_traffic("jacobi5", 16384, 16384, 4) == (None, None)
+    assert bench.measured_dram_traffic("fdtd", 4608, 4608, 3) == (None, None)
