@@ -247,13 +247,14 @@ def time_cpu_oracle(workload: str, rows: int, cols: int, target_seconds: float =
     fill(cells, 0, sample_rows, sample_rows)
 
     impl.run(workload, params, halo, cells, 0, 1)   # first touch, thread start-up
-    t0 = time.perf_counter()
-    impl.run(workload, params, halo, cells, 0, 3)
-    per_iter = (time.perf_counter() - t0) / 3
-    iters = int(max(2, min(2000, target_seconds / max(per_iter, 1e-4))))
-    t0 = time.perf_counter()
-    impl.run(workload, params, halo, cells, 0, iters)
-    elapsed = time.perf_counter() - t0
+    iters = 4
+    while True:  # grow the sample until it runs for most of the target time (short runs are slower
+        t0 = time.perf_counter()        # per iteration, so one extrapolation undershoots)
+        impl.run(workload, params, halo, cells, 0, iters)
+        elapsed = time.perf_counter() - t0
+        if elapsed >= 0.6 * target_seconds or iters >= 4000:
+            break
+        iters = int(min(4000, max(2 * iters, 1.05 * iters * target_seconds / max(elapsed, 1e-4))))
     value = sample_rows * cols * iters / elapsed / 1e9
     return {
         "value": value, "unit": "GCell-updates/s", "cores": cores,
