@@ -111,3 +111,21 @@ def test_host_copy_workers_copy_exactly(built):
     probe = np.zeros(16, dtype=np.uint8)
     assert rt.stst_host_is_pinned(probe.ctypes.data_as(C.c_void_p), C.byref(pinned)) == 0
     assert pinned.value == 0
+
+
+def test_headers_are_plain_c_and_a_c_client_links_and_fails_loudly_without_a_device(built, tmp_path):
+    """tests/cpp/c_abi_client.c, compiled as C11 with -Wall -Wextra -pedantic against include/*.h and
+    linked against the two shared libraries: the headers are valid C, the calls link, and without a
+    CUDA device the client gets an error code and a message instead of a computed result (with a
+    device it runs a small HotSpot update through the C ABI)."""
+    import subprocess
+    pkg = ROOT / "stencilstream_b200"
+    binary = tmp_path / "c_abi_client"
+    build = subprocess.run(
+        ["gcc", "-std=c11", "-Wall", "-Wextra", "-pedantic", "-Werror", f"-I{ROOT / 'include'}",
+         str(ROOT / "tests" / "cpp" / "c_abi_client.c"), "-o", str(binary), f"-L{pkg}",
+         "-lstst_workloads", "-lstst_rt", f"-Wl,-rpath,{pkg}"], capture_output=True, text=True)
+    assert build.returncode == 0, build.stderr
+    run = subprocess.run([str(binary)], capture_output=True, text=True, timeout=120)
+    assert run.returncode == 0, run.stdout + run.stderr
+    assert run.stdout.startswith("no device: status -4") or run.stdout.startswith("centre temp")
