@@ -129,3 +129,18 @@ def test_headers_are_plain_c_and_a_c_client_links_and_fails_loudly_without_a_dev
     run = subprocess.run([str(binary)], capture_output=True, text=True, timeout=120)
     assert run.returncode == 0, run.stdout + run.stderr
     assert run.stdout.startswith("no device: status -4") or run.stdout.startswith("centre temp")
+
+
+@pytest.mark.gpu
+def test_c_client_runs_an_update_through_the_c_abi(built, tmp_path):
+    """The same plain-C client on a machine with a CUDA device: grid upload, HotSpot update, download,
+    device-side max-norm and statistics, all through the C ABI from C code."""
+    import subprocess
+    pkg = ROOT / "stencilstream_b200"
+    binary = tmp_path / "c_abi_client"
+    subprocess.run(["gcc", "-std=c11", f"-I{ROOT / 'include'}", str(ROOT / "tests" / "cpp" / "c_abi_client.c"),
+                    "-o", str(binary), f"-L{pkg}", "-lstst_workloads", "-lstst_rt", f"-Wl,-rpath,{pkg}"],
+                   check=True)
+    run = subprocess.run([str(binary)], capture_output=True, text=True, timeout=300)
+    assert run.returncode == 0, run.stdout + run.stderr
+    assert run.stdout.startswith("centre temp") and "pass-through planes 0x2" in run.stdout
