@@ -145,15 +145,17 @@ template <typename F> struct SweepLauncher {
             Layout::n_planes >= 32 ? ~0u : ((1u << Layout::n_planes) - 1u);
         unsigned single_planes = 0;
         if (spec) {
-            if constexpr (!speculation_capable<F>())
+            if constexpr (speculation_capable<F>()) {
+                for (unsigned q = 0; q < n_sub && q < max_spec_subiterations; q++)
+                    geo.keep[q] = spec->probe ? 0u : (spec->keep[q] & all_planes);
+                geo.probe = spec->probe ? 1u : 0u;
+                geo.spec_flags = spec->flags;
+                single_planes = spec->probe ? 0u : spec->single_planes(n_sub, all_planes);
+                if (single_planes != plan.single_planes)
+                    throw std::logic_error("StencilStream-B200: plan and speculation masks disagree");
+            } else {
                 throw std::logic_error("StencilStream-B200: speculation on an incapable functor");
-            for (unsigned q = 0; q < n_sub && q < max_spec_subiterations; q++)
-                geo.keep[q] = spec->probe ? 0u : (spec->keep[q] & all_planes);
-            geo.probe = spec->probe ? 1u : 0u;
-            geo.spec_flags = spec->flags;
-            single_planes = spec->probe ? 0u : spec->single_planes(n_sub, all_planes);
-            if (single_planes != plan.single_planes)
-                throw std::logic_error("StencilStream-B200: plan and speculation masks disagree");
+            }
         }
         geo.iteration0 = iteration0;
         const unsigned out_rows = unsigned(region.out_row_hi - region.out_row_lo);

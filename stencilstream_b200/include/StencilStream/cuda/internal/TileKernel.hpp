@@ -592,10 +592,11 @@ sweep_rows(F const &tf, typename F::Cell const &halo_value,
                     bool differs = false;
 #pragma unroll
                     for (int i = 0; i < CW; i++) {
-                        const int gx = gx0 + c0 + i;
                         bool in_grid = true;
-                        if constexpr (!kInterior)
+                        if constexpr (!kInterior) {
+                            const int gx = gx0 + c0 + i;
                             in_grid = gy >= 0 && gy < int(geo.grid_h) && gx >= 0 && gx < int(geo.grid_w);
+                        }
                         if (in_grid)
                             differs |= bits_differ(L::template get<I>(result[i]),
                                                    L::template get<I>(win[(top + R) % DW][R + i]));
