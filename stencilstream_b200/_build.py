@@ -87,18 +87,37 @@ def build_runtime(force: bool = False, verbose: bool = False) -> Path:
     return target
 
 
+# The workloads library: the C entry points (workloads.cu) plus one translation unit per group of
+# transition functions, so that nvcc compiles the kernel templates of the groups in parallel.
+WORKLOAD_UNITS = ["workloads.cu", "workloads_light.cu", "workloads_hotspot.cu", "workloads_fdtd.cu",
+                  "workloads_convection.cu", "workloads_kat.cu"]
+
+
+def _compile_and_link_workloads(target: Path, extra_flags, verbose: bool) -> None:
+    from concurrent.futures import ThreadPoolExecutor
+
+    obj_dir = ROOT / "build" / "obj" / target.stem
+    obj_dir.mkdir(parents=True, exist_ok=True)
+    compile_flags = [f for f in NVCC_COMMON if f != "-shared"]
+
+    def compile_unit(name):
+        obj = obj_dir / (Path(name).stem + ".o")
+        _run([_nvcc(), *compile_flags, *ARCH_FLAGS, *extra_flags, f"-I{PKG / 'csrc'}", "-c",
+              PKG / "csrc" / name, "-o", obj], verbose)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=len(WORKLOAD_UNITS)) as pool:
+        objects = list(pool.map(compile_unit, WORKLOAD_UNITS))
+    _run([_nvcc(), *ARCH_FLAGS, "-shared", *objects, "-o", target, f"-L{PKG}", "-lstst_rt", "-Xlinker",
+          "-rpath,$ORIGIN"], verbose)
+
+
 def build_workloads(strict: bool = False, force: bool = False, verbose: bool = False) -> Path:
     build_runtime(force=force, verbose=verbose)
     target = PKG / ("libstst_workloads_strict.so" if strict else "libstst_workloads.so")
-    inputs = [PKG / "csrc" / "workloads.cu", PKG / "csrc" / "workloads", PKG / "include", PKG / "compat",
-              ROOT / "include"]
+    inputs = [PKG / "csrc", PKG / "include", PKG / "compat", ROOT / "include"]
     if force or _stale(target, inputs):
-        extra = ["-fmad=false"] if strict else []
-        _run(
-            [_nvcc(), *NVCC_COMMON, *ARCH_FLAGS, *extra, PKG / "csrc" / "workloads.cu", "-o", target,
-             f"-L{PKG}", "-lstst_rt", "-Xlinker", "-rpath,$ORIGIN"],
-            verbose,
-        )
+        _compile_and_link_workloads(target, ["-fmad=false"] if strict else [], verbose)
     return target
 
 
@@ -107,8 +126,7 @@ def build_variant(tag: str, extra_flags, verbose: bool = False) -> Path:
     stencilstream_b200/libstst_workloads_<tag>.so, selected at run time by STST_WORKLOADS_LIB."""
     build_runtime(verbose=verbose)
     target = PKG / f"libstst_workloads_{tag}.so"
-    _run([_nvcc(), *NVCC_COMMON, *ARCH_FLAGS, *extra_flags, PKG / "csrc" / "workloads.cu", "-o", target,
-          f"-L{PKG}", "-lstst_rt", "-Xlinker", "-rpath,$ORIGIN"], verbose)
+    _compile_and_link_workloads(target, list(extra_flags), verbose)
     return target
 
 

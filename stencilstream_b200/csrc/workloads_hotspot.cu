@@ -1,0 +1,12 @@
+/*
+ * libstst_workloads — instantiates the header-only B200 backend (StencilStream/cuda/*.hpp) for the
+ * "hotspot" transition functions of workloads/functors.hpp. One translation unit per group so that
+ * nvcc compiles the kernel templates of the groups in parallel; see workloads/model.hpp.
+ */
+#include "workloads/model.hpp"
+
+namespace stst_model {
+void register_hotspot(std::vector<WorkloadEntry> &entries) {
+    entries.push_back(make_entry<HotspotRule, stst_hotspot_params>("hotspot"));
+}
+} // namespace stst_model

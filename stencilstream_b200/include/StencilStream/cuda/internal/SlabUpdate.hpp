@@ -58,7 +58,8 @@ namespace internal {
 
 #if defined(__CUDACC__)
 /// Raise a flag in (possibly remote) device memory once everything before it in the stream is done.
-__global__ void raise_flag_kernel(volatile unsigned *flag, unsigned value) {
+/// (A template only so that this header can be included in several translation units.)
+template <int = 0> __global__ void raise_flag_kernel(volatile unsigned *flag, unsigned value) {
     __threadfence_system();
     *flag = value;
     __threadfence_system();
@@ -470,7 +471,8 @@ template <typename F> class SlabUpdate {
     void raise_flag(int s, unsigned value) {
 #if defined(__CUDACC__)
         select_device();
-        raise_flag_kernel<<<1, 1, 0, static_cast<cudaStream_t>(boundary_stream)>>>(peer_flag(s), value);
+        raise_flag_kernel<><<<1, 1, 0, static_cast<cudaStream_t>(boundary_stream)>>>(peer_flag(s),
+                                                                                     value);
         if (cudaGetLastError() != cudaSuccess)
             throw std::runtime_error("StencilStream-B200: flag kernel launch failed");
         n_launches++;
