@@ -36,6 +36,9 @@ class Oracle:
             self.lib.oracle_run_window.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                                    C.c_void_p] + [C.c_size_t] * 6
             self.lib.oracle_run_window.restype = C.c_int
+        self.lib.oracle_run_window2d.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                 C.c_void_p] + [C.c_size_t] * 8
+        self.lib.oracle_run_window2d.restype = C.c_int
 
     def run(self, workload: str, params, halo, cells: np.ndarray, iteration_offset: int,
             n_iterations: int) -> np.ndarray:
@@ -82,13 +85,58 @@ def _run_window(self, workload: str, params, halo, cells: np.ndarray, row0: int,
 Oracle.run_window = _run_window
 
 
+def _run_window2d(self, workload: str, params, halo, cells: np.ndarray, row0: int, col0: int,
+                  global_rows: int, global_cols: int, iteration_offset: int,
+                  n_iterations: int) -> np.ndarray:
+    """`Oracle.run` on the crop rows [row0, row0 + cells.shape[0]) x columns [col0, col0 +
+    cells.shape[1]) of a `global_rows` x `global_cols` grid (both oracles): transition functions see
+    global coordinates, `halo` beyond the crop. Exact further than n * n_sub * radius cells from every
+    crop edge that is not a grid border."""
+    cells = np.ascontiguousarray(cells)
+    out = np.empty_like(cells)
+    halo_arr = None
+    if halo is not None:
+        halo_arr = np.zeros((), dtype=cells.dtype)
+        halo_arr[()] = halo
+    status = self.lib.oracle_run_window2d(
+        workload.encode(), C.addressof(params) if params is not None else None,
+        halo_arr.ctypes.data if halo_arr is not None else None, cells.ctypes.data, out.ctypes.data,
+        cells.shape[0], cells.shape[1], int(row0), int(col0), int(global_rows), int(global_cols),
+        int(iteration_offset), int(n_iterations))
+    if status != 0:
+        raise RuntimeError(f"oracle_run_window2d({workload}) failed: "
+                           f"{self.lib.oracle_last_error().decode()}")
+    return out
+
+
+Oracle.run_window2d = _run_window2d
+
+
+def host_threads() -> int:
+    """Host cores this process may run on."""
+    import os
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def set_threads(n: int | None = None) -> int:
+    """Make the oracles' OpenMP loops use `n` threads (default: every core this process may run on)
+    whatever OMP_NUM_THREADS says — torchrun exports OMP_NUM_THREADS=1 to its workers, which once
+    made a "32-core" CPU baseline run on one thread. Returns omp_get_max_threads() afterwards."""
+    n = int(n or host_threads())
+    gomp = C.CDLL("libgomp.so.1", mode=C.RTLD_GLOBAL)
+    gomp.omp_set_num_threads(n)
+    gomp.omp_get_max_threads.restype = C.c_int
+    return int(gomp.omp_get_max_threads())
+
+
 def build(verbose: bool = False) -> None:
     """Build whatever oracle can be built on this machine."""
-    import sys
-    sys.path.insert(0, str(HERE.parent))
-    from stencilstream_b200 import _build
-    _build.build_oracle_port(verbose=verbose)
-    _build.build_oracle_ref(verbose=verbose)
+    from . import recipes
+    recipes.build_oracle_port(verbose=verbose)
+    recipes.build_oracle_ref(verbose=verbose)
 
 
 def port() -> Oracle:

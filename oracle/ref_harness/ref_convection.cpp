@@ -30,7 +30,7 @@ ORACLE_EXPORT int oracle_ref_convection_pt(ORACLE_REF_SIGNATURE) {
     return oracle_ref::run_cpu_backend(kernel,
                                        oracle_ref::cell_or_default<ThermalConvectionCell>(halo),
                                        cells_in, cells_out, rows, cols, iteration_offset,
-                                       n_iterations);
+                                       n_iterations, window);
 }
 
 ORACLE_EXPORT int oracle_ref_convection_thermal(ORACLE_REF_SIGNATURE) {
@@ -40,5 +40,5 @@ ORACLE_EXPORT int oracle_ref_convection_thermal(ORACLE_REF_SIGNATURE) {
     return oracle_ref::run_cpu_backend(kernel,
                                        oracle_ref::cell_or_default<ThermalConvectionCell>(halo),
                                        cells_in, cells_out, rows, cols, iteration_offset,
-                                       n_iterations);
+                                       n_iterations, window);
 }

@@ -9,5 +9,5 @@ ORACLE_EXPORT int oracle_ref_conway(ORACLE_REF_SIGNATURE) {
     (void)params;
     return oracle_ref::run_cpu_backend(ConwayKernel(), oracle_ref::cell_or_default<bool>(halo),
                                        cells_in, cells_out, rows, cols, iteration_offset,
-                                       n_iterations);
+                                       n_iterations, window);
 }

@@ -55,7 +55,7 @@ ORACLE_EXPORT int oracle_ref_fdtd(ORACLE_REF_SIGNATURE) {
     KernelImpl kernel = make_kernel(*static_cast<const stst_fdtd_params *>(params));
     return oracle_ref::run_cpu_backend(kernel, oracle_ref::cell_or_default<CellImpl>(halo),
                                        cells_in, cells_out, rows, cols, iteration_offset,
-                                       n_iterations);
+                                       n_iterations, window);
 }
 
 // Derive the functor constants, grid size and step counts from an experiment JSON file exactly as

@@ -13,5 +13,5 @@ ORACLE_EXPORT int oracle_ref_hotspot(ORACLE_REF_SIGNATURE) {
     HotspotKernel kernel{.Rx_1 = p->Rx_1, .Ry_1 = p->Ry_1, .Rz_1 = p->Rz_1, .Cap_1 = p->Cap_1};
     return oracle_ref::run_cpu_backend(kernel, oracle_ref::cell_or_default<HotspotCell>(halo),
                                        cells_in, cells_out, rows, cols, iteration_offset,
-                                       n_iterations);
+                                       n_iterations, window);
 }

@@ -37,26 +37,26 @@ ORACLE_EXPORT int oracle_ref_jacobi5(ORACLE_REF_SIGNATURE) {
     const auto *p = static_cast<const stst_jacobi5_params *>(params);
     Jacobi5General kernel = make_from_coefficients<Jacobi5General>(p->coef, 5);
     return oracle_ref::run_cpu_backend(kernel, oracle_ref::cell_or_default<float>(halo), cells_in,
-                                       cells_out, rows, cols, iteration_offset, n_iterations);
+                                       cells_out, rows, cols, iteration_offset, n_iterations, window);
 }
 
 ORACLE_EXPORT int oracle_ref_jacobi9(ORACLE_REF_SIGNATURE) {
     const auto *p = static_cast<const stst_jacobi9_params *>(params);
     Jacobi9General kernel = make_from_coefficients<Jacobi9General>(&p->coef[0][0], 9);
     return oracle_ref::run_cpu_backend(kernel, oracle_ref::cell_or_default<float>(halo), cells_in,
-                                       cells_out, rows, cols, iteration_offset, n_iterations);
+                                       cells_out, rows, cols, iteration_offset, n_iterations, window);
 }
 
 ORACLE_EXPORT int oracle_ref_jacobi_r2(ORACLE_REF_SIGNATURE) {
     stst_workloads::JacobiStarRule<2> rule;
     rule.p = *static_cast<const stst_jacobi_star_params *>(params);
     return oracle_ref::run_cpu_backend(rule, oracle_ref::cell_or_default<float>(halo), cells_in,
-                                       cells_out, rows, cols, iteration_offset, n_iterations);
+                                       cells_out, rows, cols, iteration_offset, n_iterations, window);
 }
 
 ORACLE_EXPORT int oracle_ref_jacobi_r3(ORACLE_REF_SIGNATURE) {
     stst_workloads::JacobiStarRule<3> rule;
     rule.p = *static_cast<const stst_jacobi_star_params *>(params);
     return oracle_ref::run_cpu_backend(rule, oracle_ref::cell_or_default<float>(halo), cells_in,
-                                       cells_out, rows, cols, iteration_offset, n_iterations);
+                                       cells_out, rows, cols, iteration_offset, n_iterations, window);
 }

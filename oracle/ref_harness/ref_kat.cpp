@@ -11,12 +11,12 @@ ORACLE_EXPORT int oracle_ref_kat(ORACLE_REF_SIGNATURE) {
     (void)params;
     return oracle_ref::run_cpu_backend(FPGATransFunc<1>(), oracle_ref::cell_or_default<Cell>(halo),
                                        cells_in, cells_out, rows, cols, iteration_offset,
-                                       n_iterations);
+                                       n_iterations, window);
 }
 
 ORACLE_EXPORT int oracle_ref_kat_r2(ORACLE_REF_SIGNATURE) {
     (void)params;
     return oracle_ref::run_cpu_backend(FPGATransFunc<2>(), oracle_ref::cell_or_default<Cell>(halo),
                                        cells_in, cells_out, rows, cols, iteration_offset,
-                                       n_iterations);
+                                       n_iterations, window);
 }

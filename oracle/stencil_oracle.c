@@ -17,7 +17,7 @@
  * from it (tests/golden/generate.py). The reference itself ships no numeric golden files for this
  * path; its self-checking test functor (tests/TransFuncs.hpp) is restated below as "kat".
  *
- * Build: gcc -std=c11 -O2 -ffp-contract=off -fopenmp -fPIC -shared (see stencilstream_b200/_build.py).
+ * Build: gcc -std=c11 -O2 -ffp-contract=off -fopenmp -fPIC -shared (see oracle/recipes.py).
  * -ffp-contract=off keeps a*b+c as two rounded operations, like the reference oracle build.
  */
 #include <math.h>
@@ -338,18 +338,20 @@ const char *oracle_last_error(void) { return g_error; }
 const char *oracle_kind(void) { return "port"; }
 
 /* One sweep: reference StencilStream/cpu/StencilUpdate.hpp:199-221. */
-/* `rows` x `cols` cells are held; they are rows [row0, row0 + rows) of a grid of `global_rows` rows
- * (row0 = 0, global_rows = rows for a whole grid). */
+/* `rows` x `cols` cells are held; they are rows [row0, row0 + rows) x columns [col0, col0 + cols) of
+ * a grid of `global_rows` x `global_cols` cells (row0 = col0 = 0 and global = held extent for a whole
+ * grid). */
 static void sweep(const workload_def *w, const void *params, const unsigned char *halo,
                   const unsigned char *src, unsigned char *dst, size_t rows, size_t cols,
-                  size_t row0, size_t global_rows, size_t i_iter, size_t i_subiter) {
+                  size_t row0, size_t col0, size_t global_rows, size_t global_cols, size_t i_iter,
+                  size_t i_subiter) {
     const int radius = w->radius;
     const size_t cb = w->cell_bytes;
     stencil_view proto;
     memset(&proto, 0, sizeof(proto));
     proto.radius = radius;
     proto.grid_range[0] = global_rows;
-    proto.grid_range[1] = cols;
+    proto.grid_range[1] = global_cols;
     proto.iteration = i_iter;
     proto.subiteration = i_subiter;
     if (w->tdv)
@@ -360,7 +362,7 @@ static void sweep(const workload_def *w, const void *params, const unsigned char
         stencil_view st = proto;
         for (size_t c = 0; c < cols; c++) {
             st.id[0] = row0 + (size_t)r;
-            st.id[1] = c;
+            st.id[1] = col0 + c;
             for (int rel_r = 0; rel_r < 2 * radius + 1; rel_r++) {
                 for (int rel_c = 0; rel_c < 2 * radius + 1; rel_c++) {
                     /* in-grid test exactly as :205-208 (unsigned arithmetic, shifted by radius) */
@@ -387,7 +389,8 @@ static void sweep(const workload_def *w, const void *params, const unsigned char
  */
 static int run_rows(const char *workload, const void *params, const void *halo,
                     const void *cells_in, void *cells_out, size_t rows, size_t cols, size_t row0,
-                    size_t global_rows, size_t iteration_offset, size_t n_iterations) {
+                    size_t col0, size_t global_rows, size_t global_cols, size_t iteration_offset,
+                    size_t n_iterations) {
     const workload_def *w = NULL;
     for (size_t i = 0; i < sizeof(workloads) / sizeof(workloads[0]); i++)
         if (strcmp(workloads[i].name, workload) == 0)
@@ -418,7 +421,7 @@ static int run_rows(const char *workload, const void *params, const void *halo,
     unsigned char *dst = b;
     for (size_t i_iter = 0; i_iter < n_iterations; i_iter++) {
         for (size_t i_sub = 0; i_sub < (size_t)w->n_subiterations; i_sub++) {
-            sweep(w, params, halo_cell, src, dst, rows, cols, row0, global_rows,
+            sweep(w, params, halo_cell, src, dst, rows, cols, row0, col0, global_rows, global_cols,
                   iteration_offset + i_iter, i_sub);
             if (i_iter == 0 && i_sub == 0) {
                 src = b;
@@ -439,7 +442,7 @@ static int run_rows(const char *workload, const void *params, const void *halo,
 int oracle_run(const char *workload, const void *params, const void *halo, const void *cells_in,
                void *cells_out, size_t rows, size_t cols, size_t iteration_offset,
                size_t n_iterations) {
-    return run_rows(workload, params, halo, cells_in, cells_out, rows, cols, 0, rows,
+    return run_rows(workload, params, halo, cells_in, cells_out, rows, cols, 0, 0, rows, cols,
                     iteration_offset, n_iterations);
 }
 
@@ -458,6 +461,25 @@ int oracle_run_window(const char *workload, const void *params, const void *halo
         g_error = "window exceeds the grid";
         return -2;
     }
-    return run_rows(workload, params, halo, cells_in, cells_out, rows, cols, row0, global_rows,
-                    iteration_offset, n_iterations);
+    return run_rows(workload, params, halo, cells_in, cells_out, rows, cols, row0, 0, global_rows,
+                    cols, iteration_offset, n_iterations);
+}
+
+/*
+ * The two-dimensional form: `cells_in` holds rows [row0, row0 + rows) x columns [col0, col0 + cols)
+ * of a global_rows x global_cols grid. Same exactness rule in both directions; a crop edge that
+ * coincides with the grid's border is exact (the halo really is there). Used by the full-size parity
+ * tests (tests/window_oracle.py) to check windows of 16384^2 results against a crop that contains the
+ * window's whole domain of dependence.
+ */
+int oracle_run_window2d(const char *workload, const void *params, const void *halo,
+                        const void *cells_in, void *cells_out, size_t rows, size_t cols, size_t row0,
+                        size_t col0, size_t global_rows, size_t global_cols,
+                        size_t iteration_offset, size_t n_iterations) {
+    if (row0 + rows > global_rows || col0 + cols > global_cols) {
+        g_error = "window exceeds the grid";
+        return -2;
+    }
+    return run_rows(workload, params, halo, cells_in, cells_out, rows, cols, row0, col0, global_rows,
+                    global_cols, iteration_offset, n_iterations);
 }

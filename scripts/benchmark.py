@@ -192,7 +192,7 @@ NCU_METRICS = [  # scripts/benchmark-common.jl:246-283
 def ncu_metrics(args):
     rows, cols = args.rows or 16384, args.cols or args.rows or 16384
     print("ncu --csv --clock-control none -k regex:fused_sweep --metrics " + ",".join(NCU_METRICS) +
-          f" python scratch/one.py --workload {args.workload} --rows {rows} --cols {cols} --iters 24")
+          f" python scripts/run_one.py --workload {args.workload} --rows {rows} --cols {cols} --iters 24")
 
 
 def main():

@@ -1,5 +1,5 @@
 import argparse, os, sys, threading, time, subprocess
-sys.path.insert(0, '.')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 import bench
 from stencilstream_b200 import Grid, Params, StencilUpdate
 ap = argparse.ArgumentParser()

@@ -1,6 +1,6 @@
 """Time Grid.max_abs (five convection norms) against the accessor route it replaces."""
 import sys, time
-sys.path.insert(0, '.')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 import numpy as np
 import bench
 from stencilstream_b200 import Grid

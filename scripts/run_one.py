@@ -1,6 +1,6 @@
 """Run one configuration a few times (for ncu / quick timing)."""
 import argparse, os, sys
-sys.path.insert(0, '.')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 import bench
 from stencilstream_b200 import Grid, Params, StencilUpdate, workload_info
 ap = argparse.ArgumentParser()

@@ -1,6 +1,6 @@
 """Tuning sweep: GCell-updates/s for one workload over fusion depth / CTA shape / tile rows."""
 import argparse, itertools, os, sys, time
-sys.path.insert(0, '.')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 import numpy as np
 import bench
 from stencilstream_b200 import Grid, Params, StencilUpdate, workload_info

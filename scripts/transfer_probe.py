@@ -1,6 +1,6 @@
 """Probe host<->device transfer rates of Grid uploads/downloads and the box's pinnable-memory limit."""
 import ctypes as C, os, sys, time
-sys.path.insert(0, '.')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 import numpy as np
 import bench
 from stencilstream_b200 import Grid, _native

@@ -1,14 +1,12 @@
 """Build recipes for the native parts of StencilStream-B200.
 
-Everything is built in-tree with explicit compiler invocations (nvcc for sm_100a, gcc/g++ for the CPU
-oracle) so that the resulting shared objects travel with the repository snapshot to the GPU box:
+Everything is built in-tree with explicit compiler invocations (nvcc for sm_100a) so that the resulting shared objects travel with the repository snapshot to the GPU box:
 
   stencilstream_b200/libstst_rt.so                 C-ABI device runtime           (csrc/stst_rt.cu)
   stencilstream_b200/libstst_workloads.so          generation loop + example functors, default flags
   stencilstream_b200/libstst_workloads_strict.so   same, -fmad=false (bit-parity diagnosis build)
-  oracle/liboracle_port.so                         plain-C restatement of the reference algorithm
-  oracle/_ref/liboracle_ref.so                     the reference's own cpu backend + example sources,
-                                                   compiled in place from /root/reference (if present)
+
+(The CPU parity oracles are test infrastructure and are built by oracle/recipes.py.)
 
 A target is rebuilt when it is missing or older than any of its inputs.
 """
@@ -130,18 +128,6 @@ def build_variant(tag: str, extra_flags, verbose: bool = False) -> Path:
     return target
 
 
-def build_oracle_port(force: bool = False, verbose: bool = False) -> Path:
-    target = ORACLE / "liboracle_port.so"
-    inputs = [ORACLE / "stencil_oracle.c", ROOT / "include" / "stst_workloads.h"]
-    if force or _stale(target, inputs):
-        _run(
-            ["gcc", "-std=c11", "-O2", "-ffp-contract=off", "-fopenmp", "-fPIC", "-shared",
-             f"-I{ROOT / 'include'}", inputs[0], "-o", target, "-lm"],
-            verbose,
-        )
-    return target
-
-
 def _json_include() -> Path | None:
     """nlohmann/json 3.11.3 (the version the reference pins) ships inside cudnn_frontend's headers."""
     import sysconfig
@@ -157,50 +143,16 @@ def reference_available() -> bool:
     return (REFERENCE / "StencilStream" / "cpu" / "StencilUpdate.hpp").exists()
 
 
-_REF_GLOBALS = ["exception_handler", "description", "usage", "write_output", "read_input",
-                "save_frame"]
-
-
-def build_oracle_ref(force: bool = False, verbose: bool = False) -> Path | None:
-    """Compile the reference's own cpu backend and example functors, in place, into oracle/_ref."""
-    target = ORACLE / "_ref" / "liboracle_ref.so"
-    if not reference_available():
-        return target if target.exists() else None
-    sources = sorted((ORACLE / "ref_harness").glob("*.cpp"))
-    inputs = [*sources, ORACLE / "ref_harness", PKG / "compat", ROOT / "include" / "stst_workloads.h"]
-    if force or _stale(target, inputs):
-        target.parent.mkdir(parents=True, exist_ok=True)
-        json_inc = _json_include()
-        flags = ["-std=c++20", "-O2", "-ffp-contract=off", "-fopenmp", "-fPIC", "-w",
-                 "-fvisibility=hidden",
-                 "-DSTENCILSTREAM_BACKEND_CPU=1", f"-DSTST_REFERENCE_DIR=\"{REFERENCE}\"",
-                 f"-I{PKG / 'compat'}", f"-I{REFERENCE}", f"-I{ROOT / 'include'}",
-                 f"-I{ORACLE / 'ref_harness'}"]
-        if json_inc is not None:
-            flags.append(f"-I{json_inc}")
-        objects = []
-        for src in sources:
-            obj = target.parent / (src.stem + ".o")
-            # The example sources define same-named globals (`exception_handler`, `description`,
-            # ...): give the known ones a per-translation-unit name.
-            renames = [f"-D{name}={name}_{src.stem}" for name in _REF_GLOBALS]
-            _run(["g++", *flags, *renames, "-c", src, "-o", obj], verbose)
-            objects.append(obj)
-        _run(["g++", "-shared", "-fopenmp", *objects, "-o", target], verbose)
-    return target
-
-
 def build_all(force: bool = False, verbose: bool = False) -> dict:
+    """The product libraries (runtime + the two workloads builds). The CPU oracles are test
+    infrastructure with their own recipe, oracle/recipes.py."""
     from concurrent.futures import ThreadPoolExecutor
 
     out = {"runtime": build_runtime(force=force, verbose=verbose)}
-    # The two workloads libraries and the oracles are independent: compile them side by side.
-    with ThreadPoolExecutor(max_workers=4) as pool:
+    with ThreadPoolExecutor(max_workers=2) as pool:
         jobs = {
             "workloads": pool.submit(build_workloads, False, force, verbose),
             "workloads_strict": pool.submit(build_workloads, True, force, verbose),
-            "oracle_port": pool.submit(build_oracle_port, force, verbose),
-            "oracle_ref": pool.submit(build_oracle_ref, force, verbose),
         }
         for name, job in jobs.items():
             out[name] = job.result()

@@ -44,6 +44,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <memory>
+#include <string>
 #include <vector>
 
 namespace stencil {
@@ -79,7 +80,8 @@ template <concepts::TransitionFunction F, bool split_cell_structure = false> cla
         /// Number of iterations to compute.
         std::size_t n_iterations = 1;
 
-        /// Kept for source compatibility; the CUDA device is chosen by `cuda_device`.
+        /// Kept for source compatibility (the shim's sycl::device carries no information); an update
+        /// runs on the CUDA device its source grid lives on, see `cuda_device`.
         sycl::device device = sycl::device();
 
         /// Wait for the result before returning from `operator()`.
@@ -90,7 +92,9 @@ template <concepts::TransitionFunction F, bool split_cell_structure = false> cla
 
         // ---- B200 extensions (keep last: designated initialisers of reference code stay valid) ----
 
-        /// CUDA device ordinal; negative: the device the source grid lives on.
+        /// CUDA device ordinal the update is expected to run on; negative (default): wherever the
+        /// source grid lives. An update never migrates a grid: a non-negative ordinal that differs
+        /// from the source grid's device makes `operator()` throw std::invalid_argument.
         int cuda_device = -1;
 
         /// Iterations fused per launch (temporal blocking depth k); 0 picks one automatically.
@@ -107,12 +111,20 @@ template <concepts::TransitionFunction F, bool split_cell_structure = false> cla
     StencilUpdate(StencilUpdate const &other)
         : params(other.params), n_processed_cells(other.n_processed_cells),
           walltime(other.walltime), n_launches(other.n_launches), last_plan(other.last_plan),
-          tensor_maps(), profile_events(other.profile_events) {}
+          tensor_maps(), profile_events(other.profile_events), spec_probed(other.spec_probed),
+          n_spec_redos(other.n_spec_redos) {
+        // what was observed about the transition function travels with the copy; the device words
+        // (spec_flags) are per object and allocated on first use
+        for (unsigned q = 0; q < internal::max_spec_subiterations; q++)
+            spec_keep[q] = other.spec_keep[q];
+    }
     StencilUpdate &operator=(StencilUpdate const &) = delete;
 
     ~StencilUpdate() {
         if (spec_flags)
             internal::device_free(spec_device, spec_flags, internal::default_stream(spec_device));
+        if (spec_host_flags)
+            internal::pinned_free(spec_host_flags);
     }
 
     /**
@@ -221,8 +233,13 @@ template <concepts::TransitionFunction F, bool split_cell_structure = false> cla
                 device_alloc(spec_device, sizeof(unsigned) * (max_spec_subiterations + 1),
                              source.stream));
         }
-        unsigned *host_flags =
-            static_cast<unsigned *>(pinned_alloc(sizeof(unsigned) * (max_spec_subiterations + 1)));
+        if (!spec_host_flags)
+            spec_host_flags = static_cast<unsigned *>(
+                pinned_alloc(sizeof(unsigned) * (max_spec_subiterations + 1)));
+        unsigned *host_flags = spec_host_flags;
+        // launches and profiling events of an attempt that is discarded must not be counted
+        const std::size_t launches_before = n_launches;
+        const std::size_t events_before = profile_events.size();
         auto read_flags = [&] {
             STST_RT_CHECK(stst_memcpy_d2h_async(host_flags, spec_flags,
                                                 sizeof(unsigned) * (max_spec_subiterations + 1),
@@ -235,7 +252,7 @@ template <concepts::TransitionFunction F, bool split_cell_structure = false> cla
                                             source.stream));
         };
 
-        try {
+        {
             for (;;) {
                 clear_flags();
                 GridImpl swap_a = source_grid.make_similar();
@@ -296,7 +313,6 @@ template <concepts::TransitionFunction F, bool split_cell_structure = false> cla
                 const unsigned violated = host_flags[max_spec_subiterations];
                 if (violated == 0) {
                     pass_source->get_storage().device_written();
-                    pinned_free(host_flags);
                     return *pass_source;
                 }
                 // A plane believed to pass through did change: never speculate on it again and
@@ -305,10 +321,9 @@ template <concepts::TransitionFunction F, bool split_cell_structure = false> cla
                     spec_keep[q] &= ~violated;
                 drop_unprofitable_speculation();
                 n_spec_redos++;
+                n_launches = launches_before;
+                profile_events.resize(events_before);
             }
-        } catch (...) {
-            pinned_free(host_flags);
-            throw;
         }
     }
 
@@ -347,6 +362,12 @@ template <concepts::TransitionFunction F, bool split_cell_structure = false> cla
         if (params.n_iterations == 0) {
             return source_grid;
         }
+        if (params.cuda_device >= 0 && params.cuda_device != source_grid.get_storage().device)
+            throw std::invalid_argument(
+                "StencilStream-B200: Params::cuda_device is " + std::to_string(params.cuda_device) +
+                " but the source grid lives on device " +
+                std::to_string(source_grid.get_storage().device) +
+                "; updates run where their grid is (create the grid on that device)");
         if constexpr (internal::speculation_capable<F>()) {
             if (speculation_enabled() && !speculation_has_nothing_left() &&
                 source_grid.get_grid_height() > 0 && source_grid.get_grid_width() > 0)
@@ -454,6 +475,7 @@ template <concepts::TransitionFunction F, bool split_cell_structure = false> cla
     bool spec_probed = false;
     unsigned spec_keep[internal::max_spec_subiterations] = {};
     unsigned *spec_flags = nullptr;
+    unsigned *spec_host_flags = nullptr; ///< pinned landing zone of spec_flags, allocated once
     int spec_device = 0;
     std::size_t n_spec_redos = 0;
 };

@@ -129,6 +129,7 @@ template <typename F> struct SweepLauncher {
         geo.grid_h = region.grid_h;
         geo.grid_w = region.grid_w;
         geo.buf_row0 = region.buf_row0;
+        geo.buf_rows = unsigned(region.buf_rows);
         geo.out_row_lo = region.out_row_lo;
         geo.out_row_hi = region.out_row_hi;
         geo.tile_h = region.tile_h ? std::min(region.tile_h, plan.tile_h) : plan.tile_h;

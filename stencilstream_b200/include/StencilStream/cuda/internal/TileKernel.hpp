@@ -86,6 +86,7 @@ inline constexpr unsigned max_spec_subiterations = 4;
 struct SweepGeometry {
     unsigned grid_h, grid_w; ///< global grid extent (rows, columns)
     int buf_row0;            ///< global row held in row 0 of every plane (slab origin, ghosts incl.)
+    unsigned buf_rows;       ///< rows present in every plane: [buf_row0, buf_row0 + buf_rows)
     int out_row_lo;          ///< first global row this launch has to produce
     int out_row_hi;          ///< one past the last global row this launch has to produce
     unsigned tile_h, tile_w; ///< output tile extent
@@ -390,7 +391,11 @@ __device__ __forceinline__ void stage_tile(TileView<Cell> const &tile, PlaneSet 
                     *reinterpret_cast<Pack<T, CW> *>(s) = *reinterpret_cast<const Pack<T, CW> *>(g);
                 }
             } else {
-                const bool row_in = gy >= 0 && gy < int(geo.grid_h);
+                // Inside the grid AND inside the planes that are really mapped: the last tile row of
+                // a slab launch may reach below the slab's ghost rows (the tile height does not
+                // divide the row range); what would be read there is never used for a stored cell.
+                const bool row_in = gy >= 0 && gy < int(geo.grid_h) &&
+                                    unsigned(gy - geo.buf_row0) < geo.buf_rows;
                 if (row_in && gx >= 0 && gx + CW <= int(geo.grid_w)) {
                     *reinterpret_cast<Pack<T, CW> *>(s) = *reinterpret_cast<const Pack<T, CW> *>(g);
                 } else {
@@ -466,7 +471,10 @@ sweep_rows(F const &tf, typename F::Cell const &halo_value,
     constexpr int R = int(F::stencil_radius);
     constexpr int D = 2 * R + 1;
     constexpr int WC = CW + 2 * R;
-    static_assert(R <= CW, "stencil radius must not exceed the per-thread column group width");
+    // any radius is legal (the reference's backends accept any); the unclamped edge-column loads
+    // reach R elements beyond a tile row, which the guard bytes must cover
+    static_assert(std::size_t(R) * L::max_plane_bytes() <= tile_guard_bytes,
+                  "stencil radius times the widest field exceeds the shared-memory guard");
 
     const int cols = int(in.cols);
     const int c0 = int(threadIdx.x) * CW;
@@ -511,10 +519,13 @@ sweep_rows(F const &tf, typename F::Cell const &halo_value,
 #pragma unroll
                 for (int i = 0; i < CW; i++)
                     L::template get<I>(w[R + i]) = q[i * TX];
+                // column c0 - j is element (CW - j % CW) % CW of the group ceil(j / CW) to the left,
+                // column c0 + CW - 1 + j element (j - 1) % CW of the group (j - 1) / CW + 1 to the right
 #pragma unroll
                 for (int j = 1; j <= R; j++) {
-                    L::template get<I>(w[R - j]) = q[(CW - j) * TX - 1];
-                    L::template get<I>(w[R + CW - 1 + j]) = q[(j - 1) * TX + 1];
+                    L::template get<I>(w[R - j]) =
+                        q[((CW - j % CW) % CW) * TX - (j + CW - 1) / CW];
+                    L::template get<I>(w[R + CW - 1 + j]) = q[((j - 1) % CW) * TX + (j - 1) / CW + 1];
                 }
                 return;
             }
@@ -538,6 +549,7 @@ sweep_rows(F const &tf, typename F::Cell const &halo_value,
                 constexpr bool use_shuffles = false;
 #endif
                 if constexpr (is_shuffleable_v<T> && kMode != window_reload && use_shuffles) {
+                    static_assert(R <= CW, "edge shuffles reach one lane to each side only");
                     left = shuffle_from_lower_lane(p.v[CW - j]);
                     right = shuffle_from_upper_lane(p.v[j - 1]);
                     if (lane == 0)

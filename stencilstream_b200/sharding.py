@@ -309,8 +309,7 @@ class ShardedStencilUpdate:
         if self.world == 1 or not extents:
             return local
         import torch
-        device = "cuda" if self._comm.get_backend() == "nccl" else "cpu"
-        t = torch.tensor(local, dtype=torch.float64, device=device)
+        t = torch.tensor(local, dtype=torch.float64, device=self._collective_device())
         self._comm.all_reduce(t, op=self._comm.ReduceOp.MAX)
         return [float(v) for v in t.cpu()]
 
@@ -367,12 +366,20 @@ class ShardedStencilUpdate:
             self.slab.drop_passthrough(violated)
             self.slab.restore()
 
+    def _collective_device(self):
+        """Where all-reduce operands live: THIS slab's GPU under NCCL (never torch's current device,
+        which a caller may not have set — two ranks on cuda:0 hang NCCL), host memory under gloo."""
+        import torch
+        if self._comm.get_backend() == "nccl":
+            return torch.device("cuda", self.device)
+        return torch.device("cpu")
+
     def _combine_or(self, mask: int, flag: bool) -> tuple[int, bool]:
         """(bitwise OR of `mask`, logical OR of `flag`) over all ranks."""
         if self.world == 1:
             return mask, flag
         import torch
-        device = "cuda" if self._comm.get_backend() == "nccl" else "cpu"
+        device = self._collective_device()
         # NCCL has no bitwise OR: one 0/1 entry per plane (and one for the flag), combined with MAX
         bits = torch.tensor([(mask >> i) & 1 for i in range(32)] + [int(flag)], dtype=torch.int32,
                             device=device)

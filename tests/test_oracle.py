@@ -105,3 +105,32 @@ def test_jacobi_linearity(oracle_port):
     fb = oracle_port.run("jacobi5", params, 0.0, b, 0, 3)
     fab = oracle_port.run("jacobi5", params, 0.0, a + b, 0, 3)
     assert np.array_equal(fab, fa + fb)
+
+
+WINDOWS = {  # of a 61 x 67 grid: corner, edge, interior, ragged corner, whole grid
+    "nw-corner": ((0, 9), (0, 11)), "n-edge": ((0, 7), (30, 41)), "interior": ((25, 33), (28, 40)),
+    "se-corner": ((50, 61), (55, 67)), "w-edge": ((20, 31), (0, 5)), "whole": ((0, 61), (0, 67)),
+}
+
+
+@pytest.mark.parametrize("workload", cases.GOLDEN_WORKLOADS)
+@pytest.mark.parametrize("which", ["port", "reference"])
+def test_window_oracle_equals_the_whole_grid_run(workload, which, request):
+    """Pins tests/window_oracle.py (the checker of the full-size GPU parity tests): the oracle run on
+    the domain-of-dependence crop of a window — global coordinates through oracle_run_window2d — holds
+    bit for bit what the whole-grid run holds in that window."""
+    import window_oracle
+
+    oracle = request.getfixturevalue("oracle_port" if which == "port" else "oracle_ref")
+    shape = (61, 67)
+    params, halo, cells = cases.make_case(workload, *shape, seed=3)
+    offset, n = 1, 3
+    if "kat" in workload:
+        cells = cases.kat_input(*shape, offset)
+    whole = oracle.run(workload, params, halo, cells, offset, n)
+    for name, window in WINDOWS.items():
+        got = window_oracle.expected_window(
+            oracle, workload, params, halo, lambda r0, r1, c0, c1: cells[r0:r1, c0:c1], shape, window,
+            offset, n)
+        (r0, r1), (c0, c1) = window
+        assert got.tobytes() == np.ascontiguousarray(whole[r0:r1, c0:c1]).tobytes(), (workload, name)

