@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define STST_WORKLOADS_ABI_VERSION 2
+#define STST_WORKLOADS_ABI_VERSION 3
 
 #define STST_OK 0
 #define STST_ERR_UNKNOWN_WORKLOAD (-1)
@@ -206,6 +206,11 @@ typedef struct stst_update_params {
     int cuda_device;           /* < 0: the source grid's device */
     unsigned fused_iterations; /* 0 = automatic */
     unsigned tile_rows;        /* 0 = automatic */
+    /* CUDA devices to spread ONE update over (row slabs, one per entry; an ordinal may repeat);
+     * n_cuda_devices == 0: the environment variable STST_DEVICES, else the source grid's device.
+     * Source and result grids stay single-device grids (Params::cuda_devices of the C++ API). */
+    const int *cuda_devices;
+    size_t n_cuda_devices;
 } stst_update_params;
 
 typedef struct stst_update_stats {
@@ -219,6 +224,7 @@ typedef struct stst_update_stats {
      * place instead of copying them, and how many updates had to be repeated because one changed */
     unsigned passthrough_planes;
     size_t speculation_redos;
+    size_t n_slabs; /* row slabs (GPUs) the most recent update ran on; 1 = not sharded */
 } stst_update_stats;
 
 int stst_update_create(const char *workload, const stst_update_params *params, stst_update **update);
@@ -272,6 +278,9 @@ int stst_slab_get_ipc_handle(stst_slab *slab, unsigned char handle[64]);
 int stst_slab_attach_ipc(stst_slab *slab, int side, const unsigned char handle[64],
                          size_t peer_row_lo, size_t peer_row_hi);
 int stst_slab_attach_local(stst_slab *slab, int side, stst_slab *peer);
+/* Wait for the slab's work, then forget both neighbours and unmap their memory. Every slab of a grid
+ * detaches before any of them is destroyed (a neighbour may still be pushing halo rows into it). */
+int stst_slab_detach(stst_slab *slab);
 /* Owned rows only: bytes must equal (row_hi-row_lo)*grid_cols*cell_bytes, else STST_ERR_RANGE.
  * copy_from_host is asynchronous when `cells` is pinned (stst_malloc_host / stst_host_register). */
 int stst_slab_copy_from_host(stst_slab *slab, const void *cells, size_t bytes);

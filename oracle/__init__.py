@@ -1,6 +1,9 @@
 """TEST INFRASTRUCTURE — loader for the CPU parity oracles. Never imported by the product package.
 
-Two interchangeable implementations of `oracle_run` (same C signature):
+Two interchangeable implementations of `oracle_run` (same C signature), each in two floating-point
+flavours — `-ffp-contract=off` (every operation rounded; bit-identical to the `-fmad=false` GPU build)
+and, `fma=True`, `-ffp-contract=fast -mfma` (a*b+c contracted like nvcc's default `-fmad=true` and like
+the reference's own icpx build, whose default FP model contracts):
 
   kind "reference": oracle/_ref/liboracle_ref.so — the reference's own cpu backend and example
                     functors compiled in place from /root/reference (built only where that tree
@@ -20,6 +23,8 @@ import numpy as np
 HERE = Path(__file__).resolve().parent
 PORT_LIB = HERE / "liboracle_port.so"
 REF_LIB = HERE / "_ref" / "liboracle_ref.so"
+PORT_FMA_LIB = HERE / "liboracle_port_fma.so"
+REF_FMA_LIB = HERE / "_ref" / "liboracle_ref_fma.so"
 
 
 class Oracle:
@@ -32,6 +37,7 @@ class Oracle:
         self.lib.oracle_last_error.restype = C.c_char_p
         self.lib.oracle_kind.restype = C.c_char_p
         self.kind = self.lib.oracle_kind().decode()
+        self.contracts = path.name.endswith("_fma.so")   # built with -ffp-contract=fast -mfma
         if hasattr(self.lib, "oracle_run_window"):
             self.lib.oracle_run_window.argtypes = [C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                                    C.c_void_p] + [C.c_size_t] * 6
@@ -132,29 +138,47 @@ def set_threads(n: int | None = None) -> int:
     return int(gomp.omp_get_max_threads())
 
 
+def cpu_has_fma() -> bool:
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("flags"):
+                    return " fma " in line + " "
+    except OSError:
+        pass
+    return False
+
+
 def build(verbose: bool = False) -> None:
     """Build whatever oracle can be built on this machine."""
     from . import recipes
-    recipes.build_oracle_port(verbose=verbose)
-    recipes.build_oracle_ref(verbose=verbose)
+    for fma in (False, True):
+        recipes.build_oracle_port(verbose=verbose, fma=fma)
+        recipes.build_oracle_ref(verbose=verbose, fma=fma)
 
 
-def port() -> Oracle:
-    if not PORT_LIB.exists():
+def port(fma: bool = False) -> Oracle:
+    lib = PORT_FMA_LIB if fma else PORT_LIB
+    if fma and not cpu_has_fma():
+        raise RuntimeError("this CPU has no FMA instructions: the contracting oracle cannot run here")
+    if not lib.exists():
         build()
-    return Oracle(PORT_LIB)
+    return Oracle(lib)
 
 
-def reference() -> Oracle | None:
-    """The reference-built oracle, or None where it neither exists nor can be built."""
-    if not REF_LIB.exists():
+def reference(fma: bool = False) -> Oracle | None:
+    """The reference-built oracle, or None where it neither exists nor can be built (nor run)."""
+    lib = REF_FMA_LIB if fma else REF_LIB
+    if fma and not cpu_has_fma():
+        return None
+    if not lib.exists():
         try:
             build()
         except Exception:
             return None
-    return Oracle(REF_LIB) if REF_LIB.exists() else None
+    return Oracle(lib) if lib.exists() else None
 
 
-def best() -> Oracle:
+def best(fma: bool = False) -> Oracle:
     """The reference-built oracle if available, else the C restatement."""
-    return reference() or port()
+    return reference(fma) or port(fma)

@@ -4,6 +4,11 @@
   oracle/_ref/liboracle_ref.so  the reference's own cpu backend + example sources, compiled IN PLACE from
                                 /root/reference by g++ (no reference source is copied; built only where
                                 that tree exists — the prebuilt library travels to the GPU box)
+  oracle/liboracle_port_fma.so, oracle/_ref/liboracle_ref_fma.so
+                                the same two, compiled with `-ffp-contract=fast -mfma`: g++ then contracts
+                                a*b+c into fused multiply-adds like nvcc does by default (and like the
+                                reference's own icpx build of its cuda backend, whose default FP model
+                                contracts too). The checker for the default (-fmad=true) GPU build.
   oracle/_ref/hotspot_openmp    the reference's independent Rodinia OpenMP HotSpot
                                 (examples/hotspot/hotspot_openmp.cpp), second CPU baseline for HotSpot
 
@@ -24,12 +29,15 @@ from stencilstream_b200._build import (PKG, REFERENCE, _json_include, _run, _sta
 ORACLE = ROOT / "oracle"
 
 
-def build_oracle_port(force: bool = False, verbose: bool = False) -> Path:
-    target = ORACLE / "liboracle_port.so"
+FP_FLAGS = {False: ["-ffp-contract=off"], True: ["-ffp-contract=fast", "-mfma"]}
+
+
+def build_oracle_port(force: bool = False, verbose: bool = False, fma: bool = False) -> Path:
+    target = ORACLE / ("liboracle_port_fma.so" if fma else "liboracle_port.so")
     inputs = [ORACLE / "stencil_oracle.c", ROOT / "include" / "stst_workloads.h"]
     if force or _stale(target, inputs):
         _run(
-            ["gcc", "-std=c11", "-O2", "-ffp-contract=off", "-fopenmp", "-fPIC", "-shared",
+            ["gcc", "-std=c11", "-O2", *FP_FLAGS[fma], "-fopenmp", "-fPIC", "-shared",
              f"-I{ROOT / 'include'}", inputs[0], "-o", target, "-lm"],
             verbose,
         )
@@ -40,9 +48,9 @@ _REF_GLOBALS = ["exception_handler", "description", "usage", "write_output", "re
                 "save_frame"]
 
 
-def build_oracle_ref(force: bool = False, verbose: bool = False) -> Path | None:
+def build_oracle_ref(force: bool = False, verbose: bool = False, fma: bool = False) -> Path | None:
     """Compile the reference's own cpu backend and example functors, in place, into oracle/_ref."""
-    target = ORACLE / "_ref" / "liboracle_ref.so"
+    target = ORACLE / "_ref" / ("liboracle_ref_fma.so" if fma else "liboracle_ref.so")
     if not reference_available():
         return target if target.exists() else None
     sources = sorted((ORACLE / "ref_harness").glob("*.cpp"))
@@ -50,7 +58,7 @@ def build_oracle_ref(force: bool = False, verbose: bool = False) -> Path | None:
     if force or _stale(target, inputs):
         target.parent.mkdir(parents=True, exist_ok=True)
         json_inc = _json_include()
-        flags = ["-std=c++20", "-O2", "-ffp-contract=off", "-fopenmp", "-fPIC", "-w",
+        flags = ["-std=c++20", "-O2", *FP_FLAGS[fma], "-fopenmp", "-fPIC", "-w",
                  "-fvisibility=hidden",
                  "-DSTENCILSTREAM_BACKEND_CPU=1", f"-DSTST_REFERENCE_DIR=\"{REFERENCE}\"",
                  f"-I{PKG / 'compat'}", f"-I{REFERENCE}", f"-I{ROOT / 'include'}",
@@ -59,7 +67,7 @@ def build_oracle_ref(force: bool = False, verbose: bool = False) -> Path | None:
             flags.append(f"-I{json_inc}")
         objects = []
         for src in sources:
-            obj = target.parent / (src.stem + ".o")
+            obj = target.parent / (src.stem + ("_fma.o" if fma else ".o"))
             # The example sources define same-named globals (`exception_handler`, `description`,
             # ...): give the known ones a per-translation-unit name.
             renames = [f"-D{name}={name}_{src.stem}" for name in _REF_GLOBALS]
@@ -87,10 +95,12 @@ def build_hotspot_openmp(force: bool = False, verbose: bool = False) -> Path | N
 def build_all(force: bool = False, verbose: bool = False) -> dict:
     from concurrent.futures import ThreadPoolExecutor
 
-    with ThreadPoolExecutor(max_workers=3) as pool:
+    with ThreadPoolExecutor(max_workers=5) as pool:
         jobs = {
             "oracle_port": pool.submit(build_oracle_port, force, verbose),
             "oracle_ref": pool.submit(build_oracle_ref, force, verbose),
+            "oracle_port_fma": pool.submit(build_oracle_port, force, verbose, True),
+            "oracle_ref_fma": pool.submit(build_oracle_ref, force, verbose, True),
             "hotspot_openmp": pool.submit(build_hotspot_openmp, force, verbose),
         }
         return {name: job.result() for name, job in jobs.items()}

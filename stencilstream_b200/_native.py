@@ -80,6 +80,7 @@ class UpdateParams(C.Structure):
         ("iteration_offset", C.c_size_t), ("n_iterations", C.c_size_t),
         ("blocking", C.c_int), ("profiling", C.c_int), ("cuda_device", C.c_int),
         ("fused_iterations", C.c_uint), ("tile_rows", C.c_uint),
+        ("cuda_devices", C.POINTER(C.c_int)), ("n_cuda_devices", C.c_size_t),
     ]
 
 
@@ -89,6 +90,7 @@ class UpdateStats(C.Structure):
         ("n_launches", C.c_size_t), ("fused_iterations", C.c_uint), ("tile_h", C.c_uint),
         ("tile_w", C.c_uint), ("block_x", C.c_uint), ("block_y", C.c_uint), ("use_tma", C.c_uint),
         ("smem_bytes", C.c_size_t), ("passthrough_planes", C.c_uint), ("speculation_redos", C.c_size_t),
+        ("n_slabs", C.c_size_t),
     ]
 
 
@@ -191,7 +193,7 @@ WORKLOADS_SYMBOLS = [
     "stst_update_create",
     "stst_update_set_params", "stst_update_apply", "stst_update_get_stats", "stst_update_destroy",
     "stst_slab_create", "stst_slab_destroy", "stst_slab_get_info", "stst_slab_get_ipc_handle",
-    "stst_slab_attach_ipc", "stst_slab_attach_local", "stst_slab_copy_from_host",
+    "stst_slab_attach_ipc", "stst_slab_attach_local", "stst_slab_detach", "stst_slab_copy_from_host",
     "stst_slab_copy_to_host", "stst_slab_copy_rows_from_host", "stst_slab_copy_rows_to_host",
     "stst_slab_exchange_halos", "stst_slab_update", "stst_slab_synchronize",
     "stst_slab_record_event",

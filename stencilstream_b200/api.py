@@ -226,6 +226,7 @@ class Params:
     cuda_device: int = -1
     fused_iterations: int = 0
     tile_rows: int = 0
+    cuda_devices: Any = None         # list of CUDA ordinals to shard one update over (None: STST_DEVICES)
 
 
 def _as_param_struct(workload: str, tf):
@@ -287,7 +288,12 @@ class StencilUpdate:
         native.cuda_device = int(p.cuda_device)
         native.fused_iterations = int(p.fused_iterations)
         native.tile_rows = int(p.tile_rows)
-        self._keepalive = (tf, halo)
+        devices = None
+        if p.cuda_devices:
+            devices = (C.c_int * len(p.cuda_devices))(*[int(d) for d in p.cuda_devices])
+            native.cuda_devices = devices
+            native.n_cuda_devices = len(p.cuda_devices)
+        self._keepalive = (tf, halo, devices)
         return native
 
     def get_params(self) -> Params:

@@ -346,6 +346,15 @@ STST_EXPORT int stst_slab_attach_local(stst_slab *slab, int side, stst_slab *pee
     });
 }
 
+STST_EXPORT int stst_slab_detach(stst_slab *slab) {
+    if (!slab)
+        return report(STST_ERR_INVALID_ARGUMENT, "null argument");
+    return guarded([&] {
+        slab->impl->detach();
+        return STST_OK;
+    });
+}
+
 namespace {
 int slab_copy_rows(stst_slab *slab, void *cells, size_t bytes, size_t first_row, size_t n_rows,
                    bool whole, bool to_device) {

@@ -130,6 +130,11 @@ template <typename F, typename ParamBlock> struct UpdateHolder final : UpdateBas
         out.cuda_device = p.cuda_device;
         out.fused_iterations = p.fused_iterations;
         out.tile_rows = p.tile_rows;
+        if (p.n_cuda_devices != 0) {
+            if (p.cuda_devices == nullptr)
+                throw std::invalid_argument("n_cuda_devices is set but cuda_devices is null");
+            out.cuda_devices.assign(p.cuda_devices, p.cuda_devices + p.n_cuda_devices);
+        }
         return out;
     }
 
@@ -164,6 +169,7 @@ template <typename F, typename ParamBlock> struct UpdateHolder final : UpdateBas
         s.smem_bytes = plan.smem_bytes;
         s.passthrough_planes = update->get_passthrough_planes();
         s.speculation_redos = update->get_n_speculation_redos();
+        s.n_slabs = update->get_n_slabs();
     }
 };
 
@@ -176,6 +182,7 @@ struct SlabBase {
     virtual void *device_base() = 0;
     virtual int device() const = 0;
     virtual void attach(int side, void *mapped, std::size_t lo, std::size_t hi) = 0;
+    virtual void detach() = 0;
     virtual void upload(const void *cells, std::size_t first_row, std::size_t n_rows) = 0;
     virtual void download(void *cells, std::size_t first_row, std::size_t n_rows) = 0;
     virtual void exchange() = 0;
@@ -239,6 +246,12 @@ template <typename F, typename ParamBlock> struct SlabHolder final : SlabBase {
     void attach(int side, void *mapped, std::size_t lo, std::size_t hi) override {
         slab->attach(side == 0 ? sc::internal::SlabSide::up : sc::internal::SlabSide::down, mapped,
                      lo, hi);
+    }
+    void detach() override {
+        slab->detach();
+        for (void *m : ipc_mappings)
+            (void)stst_ipc_close_mem_handle(m);
+        ipc_mappings.clear();
     }
     void upload(const void *cells, std::size_t first_row, std::size_t n_rows) override {
         slab->upload_rows(static_cast<const Cell *>(cells), first_row, n_rows);

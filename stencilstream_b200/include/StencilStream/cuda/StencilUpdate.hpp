@@ -37,6 +37,7 @@
 #include "internal/Launch.hpp"
 #include "internal/Planner.hpp"
 #include "internal/Runtime.hpp"
+#include "internal/SlabUpdate.hpp"
 #include "internal/TileKernel.hpp"
 
 #include <algorithm>
@@ -102,6 +103,17 @@ template <concepts::TransitionFunction F, bool split_cell_structure = false> cla
 
         /// Upper bound for the output tile height; 0 lets the planner fill shared memory.
         unsigned tile_rows = 0;
+
+        /// CUDA devices to spread one update over: the grid is cut into row slabs, one per entry
+        /// (an ordinal may appear more than once), each slab runs the generation loop on its device
+        /// and pushes its boundary rows into its neighbours over NVLink (cuda/internal/SlabUpdate.hpp).
+        /// Source and result grid stay ordinary single-device grids: the slabs are filled from the
+        /// source and gathered into the result with device-to-device copies, inside `operator()`.
+        /// Empty (default): the environment variable STST_DEVICES ("0,1,2,3" or "0-7"), else the
+        /// device of the source grid alone. The reference's updater takes one device
+        /// (reference cuda/StencilUpdate.hpp:83, :124-127); this is how a program written against
+        /// it — the unmodified examples — uses a whole 8 x B200 box.
+        std::vector<int> cuda_devices = {};
     };
 
     StencilUpdate(Params params)
@@ -174,6 +186,9 @@ template <concepts::TransitionFunction F, bool split_cell_structure = false> cla
     /// B200 extension: number of kernel launches submitted so far.
     std::size_t get_n_launches() const { return n_launches; }
 
+    /// B200 extension: number of row slabs (GPUs) the most recent call ran on (1: not sharded).
+    std::size_t get_n_slabs() const { return shards ? shards->slabs.size() : 1; }
+
     /// B200 extension: the plan used by the most recent call.
     internal::LaunchPlan const &get_last_plan() const { return last_plan; }
 
@@ -181,6 +196,8 @@ template <concepts::TransitionFunction F, bool split_cell_structure = false> cla
     /// without being copied (speculative plane pass-through), and how many times an update had to
     /// be repeated because a launch saw such a plane change.
     unsigned get_passthrough_planes() const {
+        if (shards)
+            return shards->slabs.front()->passthrough_planes();
         if (!spec_probed)
             return 0;
         unsigned m = all_planes;
@@ -368,6 +385,16 @@ template <concepts::TransitionFunction F, bool split_cell_structure = false> cla
                 " but the source grid lives on device " +
                 std::to_string(source_grid.get_storage().device) +
                 "; updates run where their grid is (create the grid on that device)");
+        {
+            const std::vector<int> devices = resolve_devices();
+            if (devices.size() > 1 && source_grid.get_grid_height() > 0 &&
+                source_grid.get_grid_width() > 0) {
+                if (ensure_shards(source_grid, devices))
+                    return run_sharded(source_grid);
+            } else {
+                shards.reset();
+            }
+        }
         if constexpr (internal::speculation_capable<F>()) {
             if (speculation_enabled() && !speculation_has_nothing_left() &&
                 source_grid.get_grid_height() > 0 && source_grid.get_grid_width() > 0)
@@ -431,6 +458,227 @@ template <concepts::TransitionFunction F, bool split_cell_structure = false> cla
         return *pass_source;
     }
 
+    // ---- one update spread over several GPUs of the box (Params::cuda_devices / STST_DEVICES) ----------
+
+    using Slab = internal::SlabUpdate<F>;
+
+    struct ShardSet {
+        ~ShardSet() {
+            // a slab may still be pushing rows into a neighbour: wait for all before freeing any
+            for (auto &slab : slabs)
+                if (slab)
+                    slab->synchronize();
+        }
+        std::vector<int> devices;
+        std::size_t grid_h = 0, grid_w = 0;
+        unsigned fused_override = 0, tile_rows = 0;
+        std::vector<std::unique_ptr<Slab>> slabs;
+        std::vector<std::unique_ptr<internal::Event>> done; ///< per slab: result rows are in place
+        bool speculating = false;
+    };
+
+    std::vector<int> resolve_devices() const {
+        if (!params.cuda_devices.empty())
+            return params.cuda_devices;
+        std::vector<int> devices;
+        const char *env = std::getenv("STST_DEVICES");
+        if (!env || !*env)
+            return devices;
+        // "0,1,2,3", "0-7" or a mixture ("0-3,6,7")
+        const std::string text(env);
+        std::size_t pos = 0;
+        while (pos < text.size()) {
+            std::size_t end = text.find(',', pos);
+            if (end == std::string::npos)
+                end = text.size();
+            const std::string item = text.substr(pos, end - pos);
+            const std::size_t dash = item.find('-', 1);
+            try {
+                if (dash == std::string::npos) {
+                    devices.push_back(std::stoi(item));
+                } else {
+                    const int lo = std::stoi(item.substr(0, dash)), hi = std::stoi(item.substr(dash + 1));
+                    for (int d = lo; d <= hi; d++)
+                        devices.push_back(d);
+                }
+            } catch (std::exception const &) {
+                throw std::invalid_argument("StencilStream-B200: cannot parse STST_DEVICES=\"" + text +
+                                            "\"");
+            }
+            pos = end + 1;
+        }
+        return devices;
+    }
+
+    /// Build (or reuse) the slabs for this grid and device list. Returns false if the grid cannot be
+    /// cut that way (fewer rows per slab than the ghost depth needs): the caller then runs unsharded.
+    bool ensure_shards(GridImpl &source_grid, std::vector<int> const &devices) {
+        using namespace internal;
+        auto &source = source_grid.get_storage();
+        if (shards && shards->devices == devices && shards->grid_h == source.height &&
+            shards->grid_w == source.width && shards->fused_override == params.fused_iterations &&
+            shards->tile_rows == params.tile_rows)
+            return true;
+        shards.reset();
+        int n_devices = 0;
+        STST_RT_CHECK(stst_device_count(&n_devices));
+        for (int d : devices)
+            if (d < 0 || d >= n_devices)
+                throw std::invalid_argument("StencilStream-B200: no CUDA device " + std::to_string(d) +
+                                            " (cuda_devices / STST_DEVICES)");
+        for (std::size_t count = std::min<std::size_t>(devices.size(), source.height); count > 1;
+             count--) {
+            auto set = std::make_unique<ShardSet>();
+            set->devices = devices;
+            set->grid_h = source.height;
+            set->grid_w = source.width;
+            set->fused_override = params.fused_iterations;
+            set->tile_rows = params.tile_rows;
+            try {
+                unsigned fused = params.fused_iterations;
+                for (int attempt = 0; attempt < 2; attempt++) {
+                    set->slabs.clear();
+                    unsigned k_min = ~0u, k_max = 0;
+                    for (std::size_t i = 0; i < count; i++) {
+                        typename Slab::Config cfg{};
+                        cfg.grid_rows = source.height;
+                        cfg.grid_cols = source.width;
+                        partition_rows(source.height, count, i, cfg.row_lo, cfg.row_hi);
+                        cfg.device = devices[i];
+                        cfg.fused_iterations = fused;
+                        cfg.tile_rows = params.tile_rows;
+                        cfg.overlap = true;
+                        set->slabs.push_back(std::make_unique<Slab>(cfg));
+                        const unsigned k = set->slabs.back()->get_plan().fused_iterations;
+                        k_min = std::min(k_min, k);
+                        k_max = std::max(k_max, k);
+                    }
+                    if (k_min == k_max)
+                        break;
+                    fused = k_min; // all slabs must fuse the same depth: it fixes the ghost rows
+                }
+            } catch (std::invalid_argument const &) {
+                continue; // a slab would own fewer rows than its neighbour's ghost depth: use fewer
+            }
+            // neighbours push into each other, the grid's device copies to and from every slab
+            for (std::size_t i = 0; i < count; i++) {
+                const int me = devices[i];
+                auto allow = [&](int a, int b) {
+                    if (a == b)
+                        return;
+                    int can = 0;
+                    STST_RT_CHECK(stst_peer_can_access(a, b, &can));
+                    if (!can)
+                        throw std::runtime_error("StencilStream-B200: devices " + std::to_string(a) +
+                                                 " and " + std::to_string(b) +
+                                                 " cannot access each other's memory");
+                    STST_RT_CHECK(stst_peer_enable(a, b));
+                };
+                if (i > 0) {
+                    allow(me, devices[i - 1]);
+                    auto const &up = set->slabs[i - 1]->get_config();
+                    set->slabs[i]->attach(SlabSide::up, set->slabs[i - 1]->device_base(), up.row_lo,
+                                          up.row_hi);
+                }
+                if (i + 1 < count) {
+                    allow(me, devices[i + 1]);
+                    auto const &down = set->slabs[i + 1]->get_config();
+                    set->slabs[i]->attach(SlabSide::down, set->slabs[i + 1]->device_base(),
+                                          down.row_lo, down.row_hi);
+                }
+                allow(me, source.device);
+                allow(source.device, me);
+                set->done.push_back(std::make_unique<Event>());
+            }
+            set->speculating = speculation_enabled();
+            if (set->speculating)
+                for (auto &slab : set->slabs)
+                    set->speculating = slab->enable_speculation(true) && set->speculating;
+            if (!set->speculating)
+                for (auto &slab : set->slabs)
+                    slab->enable_speculation(false);
+            shards = std::move(set);
+            return true;
+        }
+        return false;
+    }
+
+    /**
+     * The generation loop on row slabs, one per device: fill the slabs (owned and ghost rows) from
+     * the source grid, advance all of them pass by pass — the passes of the slabs are enqueued
+     * round-robin, so that no device's launch queue fills up with work that waits for a neighbour
+     * whose work is not enqueued yet — and gather the owned rows into the result grid. Everything is
+     * stream-ordered; the result grid's stream waits for the gather. With plane pass-through active
+     * the call ends by collecting the slabs' verification flags, and is repeated from the (never
+     * modified) source grid if any slab saw a kept plane change.
+     */
+    GridImpl run_sharded(GridImpl &source_grid) {
+        using namespace internal;
+        auto &source = source_grid.get_storage();
+        source.require_device();
+        GridImpl result = source_grid.make_similar();
+        auto &target = result.get_storage();
+        target.allocate_device();
+        Event ready;
+        const std::size_t k = shards->slabs.front()->get_plan().fused_iterations;
+        std::size_t launches_before = 0;
+        for (auto &slab : shards->slabs)
+            launches_before += slab->get_n_launches();
+
+        std::shared_ptr<Event> start, stop;
+        if (params.profiling) {
+            start = std::make_shared<Event>(true);
+            stop = std::make_shared<Event>(true);
+            start->record(source.stream);
+        }
+        for (;;) {
+            ready.record(source.stream);
+            for (auto &slab : shards->slabs)
+                slab->load_from_grid(source.planes, source.device, ready.get());
+            std::size_t iteration = params.iteration_offset, remaining = params.n_iterations;
+            while (remaining > 0) {
+                const std::size_t n_gens = std::min(remaining, k);
+                for (auto &slab : shards->slabs)
+                    slab->run(params.transition_function, params.halo_value, iteration, n_gens);
+                iteration += n_gens;
+                remaining -= n_gens;
+            }
+            unsigned violated = 0;
+            if (shards->speculating) {
+                bool useful = false;
+                for (auto &slab : shards->slabs) {
+                    violated |= slab->take_violations();
+                    useful = useful || slab->passthrough_planes() != 0;
+                }
+                if (violated == 0 && !useful) {
+                    shards->speculating = false; // nothing left to pass through: drop the protocol
+                    for (auto &slab : shards->slabs)
+                        slab->enable_speculation(false);
+                }
+            }
+            if (violated == 0)
+                break;
+            for (auto &slab : shards->slabs)
+                slab->drop_passthrough(violated);
+            n_spec_redos++;
+        }
+        for (std::size_t i = 0; i < shards->slabs.size(); i++) {
+            shards->slabs[i]->store_to_grid(target.planes, target.device, shards->done[i]->get());
+            STST_RT_CHECK(stst_stream_wait_event(target.stream, shards->done[i]->get()));
+        }
+        if (params.profiling) {
+            stop->record(target.stream);
+            profile_events.emplace_back(std::move(start), std::move(stop));
+        }
+        target.device_written();
+        last_plan = shards->slabs.front()->get_active_plan();
+        std::size_t launches_after = 0;
+        for (auto &slab : shards->slabs)
+            launches_after += slab->get_n_launches();
+        n_launches += launches_after - launches_before;
+        return result;
+    }
+
     void launch(internal::LaunchPlan const &plan, internal::GridStorage<Cell> &src,
                 internal::GridStorage<Cell> &dst, std::size_t iteration0, unsigned n_gens,
                 internal::Speculation const *spec = nullptr) {
@@ -478,6 +726,8 @@ template <concepts::TransitionFunction F, bool split_cell_structure = false> cla
     unsigned *spec_host_flags = nullptr; ///< pinned landing zone of spec_flags, allocated once
     int spec_device = 0;
     std::size_t n_spec_redos = 0;
+    // row slabs of the multi-GPU path (run_sharded); rebuilt when grid shape or device list change
+    std::unique_ptr<ShardSet> shards;
 };
 
 } // namespace cuda

@@ -33,6 +33,8 @@ struct LaunchRegion {
     int out_row_lo;          ///< global rows [out_row_lo, out_row_hi) are produced
     int out_row_hi;
     unsigned tile_h;         ///< output tile height for this launch (0: the plan's)
+    int out2_row_lo = 0;     ///< optional second row range of the same launch (a slab's other
+    int out2_row_hi = 0;     ///< boundary strip); empty unless out2_row_hi > out2_row_lo
 };
 
 /**
@@ -133,7 +135,10 @@ template <typename F> struct SweepLauncher {
         geo.out_row_lo = region.out_row_lo;
         geo.out_row_hi = region.out_row_hi;
         geo.tile_h = region.tile_h ? std::min(region.tile_h, plan.tile_h) : plan.tile_h;
+        const bool second = region.out2_row_hi > region.out2_row_lo;
         geo.tile_h = std::min(geo.tile_h, unsigned(region.out_row_hi - region.out_row_lo));
+        if (second)
+            geo.tile_h = std::min(geo.tile_h, unsigned(region.out2_row_hi - region.out2_row_lo));
         geo.tile_w = plan.tile_w;
         geo.halo = n_gens * n_sub * radius;
         geo.hpad = plan.hpad;
@@ -161,6 +166,14 @@ template <typename F> struct SweepLauncher {
         geo.iteration0 = iteration0;
         const unsigned out_rows = unsigned(region.out_row_hi - region.out_row_lo);
         const unsigned tiles_y = (out_rows + geo.tile_h - 1) / geo.tile_h;
+        geo.tiles_first = geo.tiles_x * tiles_y;
+        unsigned tiles_second = 0;
+        if (second) {
+            geo.out2_row_lo = region.out2_row_lo;
+            geo.out2_row_hi = region.out2_row_hi;
+            const unsigned rows2 = unsigned(region.out2_row_hi - region.out2_row_lo);
+            tiles_second = geo.tiles_x * ((rows2 + geo.tile_h - 1) / geo.tile_h);
+        }
 
         // Time-dependent values: evaluated on the host, exactly once per iteration
         // (reference cuda/StencilUpdate.hpp:224).
@@ -188,7 +201,7 @@ template <typename F> struct SweepLauncher {
         }
 
         const dim3 block(plan.block_x, plan.block_y, 1);
-        const dim3 grid(geo.tiles_x * tiles_y, 1, 1);
+        const dim3 grid(geo.tiles_first + tiles_second, 1, 1);
         auto submit = [&](auto kernel, std::size_t &configured_smem) {
             if (smem > configured_smem) {
                 cudaError_t err = cudaFuncSetAttribute(

@@ -17,16 +17,19 @@
  *
  *   boundary stream:  wait  flag_from_up >= e+1, flag_from_down >= e+1      (ghosts of epoch e in place)
  *                     wait  interior launch of epoch e-1
- *                     sweep the top and bottom `ghost` rows of the slab; the kernel stores them into
- *                           the own target planes AND into the neighbours' ghost rows (HaloPush)
- *                     signal neighbours: their flag_from_{down,up} = e+2
+ *                     sweep the top and bottom `ghost` rows of the slab in ONE launch; the kernel stores
+ *                           them into the own target planes AND into the neighbours' ghost rows
+ *                           (HaloPush), and its last CTA signals the neighbours:
+ *                           their flag_from_{down,up} = e+2
  *   interior stream:  wait  boundary launches of epoch e-1
  *                     sweep the remaining rows (they depend on no ghost row)
  *
  * so the exchange for the next pass overlaps the interior sweep of this one, and nothing but the
  * two small boundary launches ever waits for a neighbour. Flags are waited for with
- * cuStreamWaitValue32 (stream-ordered, no host involvement, works across processes) and raised by a
- * one-thread kernel behind the boundary sweep (system-scope fence + store). The flag protocol also
+ * cuStreamWaitValue32 (stream-ordered, no host involvement, works across processes) and raised by the
+ * boundary launch itself: every CTA fences its stores system-wide and takes an atomic ticket, the
+ * holder of the last ticket stores the flags (exchange_halos(), which copies with cudaMemcpy, still
+ * uses a one-thread kernel behind the copies). The flag protocol also
  * covers the write-after-read hazards of the ping/pong buffers: a neighbour can only write ghost rows
  * of buffer B in its epoch e+1 after it saw flag e+2, which is raised after this slab's epoch-e
  * boundary launches — the last readers of those ghost rows — have finished.
@@ -70,7 +73,9 @@ template <int = 0> __global__ void raise_flag_kernel(volatile unsigned *flag, un
 /// neighbour can address into a mapped slab knowing only that slab's row range.
 template <typename Cell> struct SlabLayout {
     using Layout = CellLayout<Cell>;
-    static constexpr std::size_t flag_bytes = 256; ///< [0]: flag_from_up, [1]: flag_from_down
+    /// [0]: flag_from_up, [1]: flag_from_down, [8]: ticket counter of the boundary launches
+    static constexpr std::size_t flag_bytes = 256;
+    static constexpr int ticket_word = 8;
 
     std::size_t width, owned_rows, ghost, buf_rows;
     std::size_t pitch[max_planes];        ///< elements between rows, per plane
@@ -298,6 +303,17 @@ template <typename F> class SlabUpdate {
         peer_row_hi[s] = row_hi;
     }
 
+    /// Forget both neighbours (after waiting for this slab's work): nothing this slab does afterwards
+    /// touches their memory, so their owners may free it. Every slab of a grid detaches before any
+    /// of them is destroyed (sharding.py: barrier, detach, barrier, destroy).
+    void detach() {
+        synchronize();
+        for (int s = 0; s < 2; s++) {
+            peer_base[s] = nullptr;
+            peer_row_lo[s] = peer_row_hi[s] = 0;
+        }
+    }
+
     // ---- data ---------------------------------------------------------------------------------------
 
     /// Replace the owned rows by `cells` (dense row-major array of whole cells, owned_rows x width).
@@ -380,6 +396,71 @@ template <typename F> class SlabUpdate {
                 static_cast<const unsigned char *>(other_planes.base[i]) + other_ghost * row_bytes,
                 owned_rows() * row_bytes, interior_stream));
         }
+        fork_streams();
+    }
+
+    /**
+     * Replace the owned AND the ghost rows by the corresponding rows of a whole grid whose planes
+     * (same row pitch as a slab's: both are "width rounded up to 128 bytes") live on `grid_device` —
+     * one contiguous device-to-device (peer) copy per plane, after `ready` (recorded on the grid's
+     * stream) has fired. Because the ghost rows come along, no exchange_halos() is needed; like it,
+     * this opens a fresh pair of epochs and is collective: every slab of the grid does it at the same
+     * point of its sequence of operations. Used by the single-process multi-GPU path of
+     * StencilUpdate (cuda/StencilUpdate.hpp, run_sharded).
+     */
+    void load_from_grid(PlaneSet const &grid_planes, int grid_device, stst_event_t ready) {
+        join_streams();
+        // The neighbours' last pass pushed into the ghost rows of the buffer that is about to be
+        // overwritten: wait until those pushes have landed (the condition a pass waits for).
+        // (A slab that has never run a pass or an exchange has no such pushes pending — and flags
+        // that still read zero.)
+        for (int s = 0; s < 2 && epoch > 0; s++) {
+            if (has_side(s))
+                STST_RT_CHECK(stst_stream_wait_value32_geq(interior_stream, my_flag(s),
+                                                           unsigned(epoch + 1)));
+        }
+        epoch += 2;
+        const int cur = int(epoch & 1);
+        const PlaneSet mine = layout.planes(base, cur);
+        const std::size_t first = cfg.row_lo >= ghost ? cfg.row_lo - ghost : 0; // global rows copied
+        const std::size_t last = std::min(cfg.grid_rows, cfg.row_hi + ghost);
+        const std::size_t into = first + ghost - cfg.row_lo; // slab row that holds global row `first`
+        if (ready)
+            STST_RT_CHECK(stst_stream_wait_event(interior_stream, ready));
+        for (std::size_t i = 0; i < Layout::n_planes; i++) {
+            if (grid_planes.pitch[i] != layout.pitch[i])
+                throw std::logic_error("StencilStream-B200: grid and slab row pitches differ");
+            const std::size_t row_bytes = layout.pitch[i] * Layout::plane_bytes(i);
+            STST_RT_CHECK(stst_memcpy_peer_async(
+                static_cast<unsigned char *>(mine.base[i]) + into * row_bytes, cfg.device,
+                static_cast<const unsigned char *>(grid_planes.base[i]) + first * row_bytes,
+                grid_device, (last - first) * row_bytes, interior_stream));
+        }
+        // the ghost rows of the new epoch are in place: what the neighbours' flags would say
+        for (int s = 0; s < 2; s++) {
+            if (has_side(s))
+                STST_RT_CHECK(stst_stream_write_value32(interior_stream, my_flag(s),
+                                                        unsigned(epoch + 1)));
+        }
+        fork_streams();
+    }
+
+    /// Copy the owned rows of the current generation into the planes of a whole grid on
+    /// `grid_device` (peer copy, one per plane) and record `done` behind the copies.
+    void store_to_grid(PlaneSet const &grid_planes, int grid_device, stst_event_t done) {
+        join_streams();
+        const PlaneSet mine = current_planes();
+        for (std::size_t i = 0; i < Layout::n_planes; i++) {
+            if (grid_planes.pitch[i] != layout.pitch[i])
+                throw std::logic_error("StencilStream-B200: grid and slab row pitches differ");
+            const std::size_t row_bytes = layout.pitch[i] * Layout::plane_bytes(i);
+            STST_RT_CHECK(stst_memcpy_peer_async(
+                static_cast<unsigned char *>(grid_planes.base[i]) + cfg.row_lo * row_bytes,
+                grid_device, static_cast<const unsigned char *>(mine.base[i]) + ghost * row_bytes,
+                cfg.device, owned_rows() * row_bytes, interior_stream));
+        }
+        if (done)
+            STST_RT_CHECK(stst_event_record(done, interior_stream));
         fork_streams();
     }
 
@@ -625,12 +706,27 @@ template <typename F> class SlabUpdate {
                                                            unsigned(epoch + 1)));
         }
 
-        auto sweep = [&](std::size_t lo, std::size_t hi, bool with_push, bool strip,
-                         stst_stream_t stream) {
+        // The boundary launch raises the neighbours' flags itself (its last CTA, see HaloPush).
+        if (pushes) {
+            push.ticket = SlabLayout<Cell>::flag(base, SlabLayout<Cell>::ticket_word);
+            push.flag_up = has_up() ? peer_flag(0) : nullptr;
+            push.flag_down = has_down() ? peer_flag(1) : nullptr;
+            push.flag_value = unsigned(epoch + 2);
+        }
+
+        // rows [lo, hi) and, optionally, [lo2, hi2) in ONE launch
+        auto sweep = [&](std::size_t lo, std::size_t hi, std::size_t lo2, std::size_t hi2,
+                         bool with_push, bool strip, stst_stream_t stream) {
+            if (hi <= lo) {       // only the second range exists
+                lo = lo2, hi = hi2;
+                lo2 = hi2 = 0;
+            }
             if (hi <= lo)
                 return;
             region.out_row_lo = int(lo);
             region.out_row_hi = int(hi);
+            region.out2_row_lo = int(lo2);
+            region.out2_row_hi = int(hi2 > lo2 ? hi2 : lo2);
             region.tile_h = strip ? unsigned(hi - lo) : 0;
             SweepLauncher<F>::launch(use_plan, tf, halo_value, src, dst,
                                      (with_push && pushes) ? &push : nullptr, region, iteration0,
@@ -640,19 +736,16 @@ template <typename F> class SlabUpdate {
 
         const bool split = cfg.overlap && pushes && owned_rows() > 2 * ghost;
         if (split) {
+            // Two launches per pass: both boundary strips (with the halo push and the flags), then
+            // the interior. (Until round 2 this was five: a launch per strip and a one-thread kernel
+            // per flag, each ~7 us of host time and, worse, four dependent launches on the path
+            // between neighbouring slabs — what limited strong scaling to small slabs.)
             const std::size_t top_hi = has_up() ? cfg.row_lo + ghost : cfg.row_lo;
             const std::size_t bottom_lo = has_down() ? cfg.row_hi - ghost : cfg.row_hi;
-            sweep(cfg.row_lo, top_hi, true, true, boundary_stream);
-            sweep(bottom_lo, cfg.row_hi, true, true, boundary_stream);
-            for (int s = 0; s < 2; s++)
-                if (has_side(s))
-                    raise_flag(s, unsigned(epoch + 2));
-            sweep(top_hi, bottom_lo, false, false, interior_stream);
+            sweep(cfg.row_lo, top_hi, bottom_lo, cfg.row_hi, true, true, boundary_stream);
+            sweep(top_hi, bottom_lo, 0, 0, false, false, interior_stream);
         } else {
-            sweep(cfg.row_lo, cfg.row_hi, true, false, boundary_stream);
-            for (int s = 0; s < 2; s++)
-                if (has_side(s))
-                    raise_flag(s, unsigned(epoch + 2));
+            sweep(cfg.row_lo, cfg.row_hi, 0, 0, true, false, boundary_stream);
         }
         epoch++;
     }

@@ -89,6 +89,9 @@ struct SweepGeometry {
     unsigned buf_rows;       ///< rows present in every plane: [buf_row0, buf_row0 + buf_rows)
     int out_row_lo;          ///< first global row this launch has to produce
     int out_row_hi;          ///< one past the last global row this launch has to produce
+    int out2_row_lo;         ///< a second row range produced by the same launch (both boundary strips of
+    int out2_row_hi;         ///< a slab in one launch); empty unless out2_row_hi > out2_row_lo
+    unsigned tiles_first;    ///< number of CTAs that work on the first range (the rest: the second)
     unsigned tile_h, tile_w; ///< output tile extent
     unsigned halo;           ///< d = n_gens * n_subiterations * radius
     unsigned hpad;           ///< column halo, d rounded up to a multiple of CW
@@ -126,6 +129,14 @@ struct HaloPush {
     int up_buf_row0, down_buf_row0;
     int up_row_hi;   ///< INT_MIN if there is nothing to push upwards
     int down_row_lo; ///< INT_MAX if there is nothing to push downwards
+    // Completion signal, raised by the launch itself: the CTA that finishes LAST (atomic ticket in
+    // own device memory) stores `flag_value` into the neighbours' flag words once every CTA's
+    // pushed rows are visible system-wide. Saves the two one-thread flag kernels (and their launch
+    // latency on the critical path between neighbouring slabs) that used to follow a boundary launch.
+    unsigned *ticket;      ///< device word, zero between launches; nullptr: the launch raises nothing
+    unsigned *flag_up;     ///< flag word inside the upper neighbour's slab (or nullptr)
+    unsigned *flag_down;   ///< flag word inside the lower neighbour's slab (or nullptr)
+    unsigned flag_value;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -463,7 +474,7 @@ sweep_rows(F const &tf, typename F::Cell const &halo_value,
            typename F::TimeDependentValue const &tdv, std::size_t iteration,
            TileView<typename F::Cell> const &in, TileView<typename F::Cell> const &out,
            bool to_global_arg, PlaneSet const &dst, HaloPush const &push, SweepGeometry const &geo,
-           int gy0, int gx0, int row_lo, int row_hi, SpecTrack &spec) {
+           int gy0, int gx0, int row_lo, int row_hi, int out_lo, int out_hi, SpecTrack &spec) {
     using Cell = typename F::Cell;
     using TDV = typename F::TimeDependentValue;
     using L = CellLayout<Cell>;
@@ -649,7 +660,7 @@ sweep_rows(F const &tf, typename F::Cell const &halo_value,
                 return;
             const int gxg = gx0 + c0;
             if constexpr (!kInterior) {
-                if (gy < geo.out_row_lo || gy >= geo.out_row_hi || gy >= int(geo.grid_h))
+                if (gy < out_lo || gy >= out_hi || gy >= int(geo.grid_h))
                     return;
             }
             auto store_row = [&](PlaneSet const &planes, int buf_row0) {
@@ -757,7 +768,7 @@ run_tile(F const &tf, typename F::Cell const &halo_value,
          TdvArray<typename F::TimeDependentValue> const &tdvs, PlaneSet const &src,
          PlaneSet const &dst, HaloPush const &push, TensorMapSet const &maps,
          SweepGeometry const &geo, unsigned char *smem, unsigned long long *mbar, int gy0,
-         int gx0) {
+         int gx0, int out_lo, int out_hi) {
     using Cell = typename F::Cell;
     using L = CellLayout<Cell>;
     constexpr int R = int(F::stencil_radius);
@@ -818,7 +829,7 @@ run_tile(F const &tf, typename F::Cell const &halo_value,
                             sweep_rows<F, CW, kInterior, kMode, decltype(store_c)::value,
                                        decltype(in_lm_c)::value, decltype(out_lm_c)::value, kTX, kSpec,
                                        kSub>(tf, halo_value, tdv, iteration, in, out, last, dst, push,
-                                             geo, gy0, gx0, lo, hi, track);
+                                             geo, gy0, gx0, lo, hi, out_lo, out_hi, track);
                         };
                         using std::false_type;
                         using std::true_type;
@@ -917,23 +928,52 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
         __syncthreads();
     }
 
-    const unsigned tx = blockIdx.x % geo.tiles_x;
-    const unsigned ty = blockIdx.x / geo.tiles_x;
-    const int tile_gy = geo.out_row_lo + int(ty * geo.tile_h);
+    // Which of the (at most two) row ranges of this launch the CTA works on.
+    unsigned tile_index = blockIdx.x;
+    int out_lo = geo.out_row_lo, out_hi = geo.out_row_hi;
+    if (tile_index >= geo.tiles_first) {
+        tile_index -= geo.tiles_first;
+        out_lo = geo.out2_row_lo;
+        out_hi = geo.out2_row_hi;
+    }
+    const unsigned tx = tile_index % geo.tiles_x;
+    const unsigned ty = tile_index / geo.tiles_x;
+    const int tile_gy = out_lo + int(ty * geo.tile_h);
     const int tile_gx = int(tx * geo.tile_w);
     const int gy0 = tile_gy - int(geo.halo);
     const int gx0 = tile_gx - int(geo.hpad);
 
     const bool interior = gy0 >= 0 && tile_gy + int(geo.tile_h + geo.halo) <= int(geo.grid_h) &&
-                          tile_gy + int(geo.tile_h) <= geo.out_row_hi && gx0 >= 0 &&
+                          tile_gy + int(geo.tile_h) <= out_hi && gx0 >= 0 &&
                           tile_gx + int(geo.tile_w + geo.hpad) <= int(geo.grid_w);
 
     if (interior) {
         run_tile<F, CW, true, kMode, kTX, kSpec>(tf, halo_value, tdvs, src, dst, push, maps, geo, smem,
-                                                 &mbar, gy0, gx0);
+                                                 &mbar, gy0, gx0, out_lo, out_hi);
     } else {
         run_tile<F, CW, false, (kMode == window_reload ? window_reload : window_shift), kTX, kSpec>(
-            tf, halo_value, tdvs, src, dst, push, maps, geo, smem, &mbar, gy0, gx0);
+            tf, halo_value, tdvs, src, dst, push, maps, geo, smem, &mbar, gy0, gx0, out_lo, out_hi);
+    }
+
+    if (geo.push && push.ticket != nullptr) {
+        // Every thread makes its stores (own planes and the neighbours' ghost rows) visible
+        // system-wide, then the CTA takes a ticket; the holder of the last ticket knows that all
+        // CTAs of the launch have passed their fence (fence / relaxed atomic / fence: release and
+        // acquire patterns of the PTX memory model) and raises the neighbours' flags.
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0 && threadIdx.y == 0) {
+            const unsigned ticket = atomicAdd(push.ticket, 1u);
+            if (ticket == gridDim.x - 1u) {
+                __threadfence_system();
+                if (push.flag_up != nullptr)
+                    *reinterpret_cast<volatile unsigned *>(push.flag_up) = push.flag_value;
+                if (push.flag_down != nullptr)
+                    *reinterpret_cast<volatile unsigned *>(push.flag_down) = push.flag_value;
+                *reinterpret_cast<volatile unsigned *>(push.ticket) = 0u; // for the next launch
+                __threadfence_system();
+            }
+        }
     }
 }
 

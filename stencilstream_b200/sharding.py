@@ -56,6 +56,7 @@ def _slab_lib(strict: bool | None = None):
         lib.stst_slab_get_ipc_handle.argtypes = [vp, C.c_char_p]
         lib.stst_slab_attach_ipc.argtypes = [vp, C.c_int, C.c_char_p, C.c_size_t, C.c_size_t]
         lib.stst_slab_attach_local.argtypes = [vp, C.c_int, vp]
+        lib.stst_slab_detach.argtypes = [vp]
         lib.stst_slab_copy_from_host.argtypes = [vp, vp, C.c_size_t]
         lib.stst_slab_copy_to_host.argtypes = [vp, vp, C.c_size_t]
         lib.stst_slab_copy_rows_from_host.argtypes = [vp, C.c_size_t, C.c_size_t, vp, C.c_size_t]
@@ -117,6 +118,10 @@ class NativeSlab:
 
     def attach_local(self, side: int, peer: "NativeSlab") -> None:
         _check(self._lib, self._lib.stst_slab_attach_local(self._handle, side, peer._handle))
+
+    def detach(self) -> None:
+        """Wait for this slab, then forget and unmap both neighbours."""
+        _check(self._lib, self._lib.stst_slab_detach(self._handle))
 
     def copy_from_host(self, cells: np.ndarray) -> None:
         arr = np.ascontiguousarray(cells, dtype=self.dtype)
@@ -397,4 +402,17 @@ class ShardedStencilUpdate:
         return self.slab.info()
 
     def close(self) -> None:
+        """Release the slab. Collective when the grid has several slabs: every slab first stops
+        touching its neighbours' memory (barrier, detach, barrier), only then is any of them freed."""
+        if self.slab is None:
+            return
+        self.slab.synchronize()
+        detach = getattr(self.slab, "detach", None)
+        if self.world > 1:
+            self._comm.barrier()
+        if detach is not None:
+            detach()
+        if self.world > 1:
+            self._comm.barrier()
         self.slab.close()
+        self.slab = None

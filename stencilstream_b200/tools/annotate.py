@@ -15,6 +15,9 @@ StencilStream/cuda/StencilUpdate.hpp:224). The sources under version control rem
 include path and CMake target stay the only hand-made differences.
 
     python -m stencilstream_b200.tools.annotate SRC [SRC ...] -o OUT_DIR
+    python -m stencilstream_b200.tools.annotate --tree SRC_DIR -o OUT_DIR    (every *.cpp/*.hpp/*.h
+                                            below SRC_DIR, same relative layout; what the CMake
+                                            module cmake/StencilStreamB200.cmake runs)
 """
 from __future__ import annotations
 
@@ -63,13 +66,33 @@ def annotate_file(src: Path, dst: Path, also=()) -> int:
     return count
 
 
+def annotate_tree(src_dir: Path, out_dir: Path, also=()) -> int:
+    """Annotated copies of every C++ source/header below `src_dir`, same relative layout. Files whose
+    annotated text is unchanged are not rewritten (keeps build-tree timestamps stable)."""
+    total = 0
+    for src in sorted(src_dir.rglob("*")):
+        if src.suffix not in (".cpp", ".hpp", ".h") or not src.is_file():
+            continue
+        dst = out_dir / src.relative_to(src_dir)
+        text, count = annotate_text(src.read_text(), also)
+        total += count
+        if not dst.exists() or dst.read_text() != text:
+            dst.parent.mkdir(parents=True, exist_ok=True)
+            dst.write_text(text)
+    return total
+
+
 def main() -> None:
     ap = argparse.ArgumentParser(description=__doc__.split("\n")[0])
-    ap.add_argument("sources", nargs="+", type=Path)
+    ap.add_argument("sources", nargs="*", type=Path)
+    ap.add_argument("--tree", type=Path, help="annotate every C++ file below this directory")
     ap.add_argument("-o", "--out-dir", type=Path, required=True)
     ap.add_argument("--also", default="", help="comma-separated names of further functions to annotate")
     args = ap.parse_args()
     also = tuple(n for n in args.also.split(",") if n)
+    if args.tree:
+        n = annotate_tree(args.tree, args.out_dir, also)
+        print(f"{args.tree} -> {args.out_dir}: {n} function(s) annotated")
     for src in args.sources:
         n = annotate_file(src, args.out_dir / src.name, also)
         print(f"{src} -> {args.out_dir / src.name}: {n} function(s) annotated")

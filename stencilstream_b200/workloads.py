@@ -306,12 +306,11 @@ class ConvectionExperiment:
         p.nx, p.ny, p.dx, p.dy, p.dt, p.DcT = self.nx, self.ny, self.dx, self.dy, dt, self.DcT
         return p
 
-    def initial_grid(self, row_lo: int = 0, row_hi: int | None = None) -> np.ndarray:
-        """Initial temperature blob (reference convection.cpp:380-397); optionally only rows
-        [row_lo, row_hi) of it (for slab-wise generation of very large grids)."""
+    def initial_temperature(self, row_lo: int = 0, row_hi: int | None = None) -> np.ndarray:
+        """The `T` field of the initial state (reference convection.cpp:380-397) for rows
+        [row_lo, row_hi); every other field starts at zero."""
         nx, ny = self.nx, self.ny
         row_hi = nx + 1 if row_hi is None else row_hi
-        cells = np.zeros((row_hi - row_lo, ny + 1), dtype=CELL_DTYPES["convection_pt"])
         x = np.arange(row_lo, row_hi, dtype=np.float64)[:, None]
         y = np.arange(ny + 1, dtype=np.float64)[None, :]
         # std::exp(-std::pow((x*dx - px)/w, 2) - std::pow((y*dy - py)/w, 2))
@@ -321,5 +320,12 @@ class ConvectionExperiment:
         T = np.where(inside, blob, 0.0)
         T = np.where(y == ny - 1, -self.deltaT / 2.0, T)
         T = np.where(y == 0, self.deltaT / 2.0, T)
-        cells["T"] = np.broadcast_to(T, cells.shape)
+        return np.broadcast_to(T, (row_hi - row_lo, ny + 1))
+
+    def initial_grid(self, row_lo: int = 0, row_hi: int | None = None) -> np.ndarray:
+        """Initial temperature blob (reference convection.cpp:380-397); optionally only rows
+        [row_lo, row_hi) of it (for slab-wise generation of very large grids)."""
+        T = self.initial_temperature(row_lo, row_hi)
+        cells = np.zeros(T.shape, dtype=CELL_DTYPES["convection_pt"])
+        cells["T"] = T
         return cells

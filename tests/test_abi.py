@@ -34,7 +34,7 @@ def test_workloads_exports_every_declared_symbol(built, strict):
     for name in names:
         assert hasattr(lib, name), f"libstst_workloads does not export {name}"
     assert sorted(_native.WORKLOADS_SYMBOLS) == names
-    assert lib.stst_workloads_abi_version() == 2
+    assert lib.stst_workloads_abi_version() == 3
 
 
 def test_registry_matches_the_python_mirror(built):

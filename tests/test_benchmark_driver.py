@@ -74,5 +74,41 @@ def test_bench_roofline_traffic_comes_from_the_committed_capture():
     # one read and one write of a 1 GiB grid per launch, within 5 % (halo re-reads hit L2; the last
     # dirty lines are still in L2 when the kernel ends)
     assert abs(traffic / (2 * 2 ** 30) - 1.0) < 0.05
-    assert bench.measured_dram_traffic("jacobi5", 16384, 16384, 4) == (None, None)
-    assert bench.measured_dram_traffic("fdtd", 4608, 4608, 3) == (None, None)
+    # a configuration without a capture reports None and says why (never a number of another plan)
+    none, why = bench.measured_dram_traffic("jacobi5", 16384, 16384, 4)
+    assert none is None and "no ncu capture" in why
+    # every index entry points at a committed summary
+    import json
+    for entry in json.loads((ROOT / "profiles" / "dram_traffic.json").read_text()):
+        assert (ROOT / entry["source"]).exists(), entry
+
+
+def test_bench_parity_window_agrees_with_a_whole_grid_oracle_run(oracle_best):
+    """bench.py's `parity` record: the window check it runs after the end-to-end steps must report
+    zero for the oracle's own whole-grid result and a clear failure for a perturbed one."""
+    import numpy as np
+    import bench
+
+    rows = cols = 256
+    iters = 12
+    for workload in ("jacobi5", "hotspot"):
+        params, halo, fill = bench.make_workload(workload, rows, cols)
+        from stencilstream_b200 import _native
+        cells = np.empty((rows, cols), dtype=_native.CELL_DTYPES[workload])
+        fill(cells, 0, rows, rows)
+        whole = oracle_best.run(workload, params, halo, cells, 0, iters)
+        record = bench.check_parity_window(workload, params, halo, fill, rows, cols, iters, 0, rows, whole)
+        assert record["rel_max_norm"] == 0.0 and record["ok"], record
+        assert record["window"] == [[32, 96], [32, 96]]
+        # a slab that owns only the lower half of the window checks that half
+        half = bench.check_parity_window(workload, params, halo, fill, rows, cols, iters, 64, 128,
+                                         whole[64:128])
+        assert half["window"][0] == [64, 96] and half["rel_max_norm"] == 0.0
+        # rows outside the window: nothing to check
+        assert bench.check_parity_window(workload, params, halo, fill, rows, cols, iters, 128, 256,
+                                         whole[128:]) is None
+        broken = whole.copy()
+        field = broken[broken.dtype.names[0]] if broken.dtype.names else broken
+        field[64, 64] *= 1.001
+        bad = bench.check_parity_window(workload, params, halo, fill, rows, cols, iters, 0, rows, broken)
+        assert not bad["ok"] and bad["rel_max_norm"] > 1e-5

@@ -67,3 +67,17 @@ def test_jacobi_example_matches_oracle(tmp_path, oracle_best):
     want = oracle_best.run("jacobi5", params, 0.0, W.jacobi_input(300, 260), 0, 37)
     assert got.tobytes() == want.tobytes()
     assert "Walltime" in (tmp_path / "out" / "stdout.txt").read_text()
+
+
+def test_unmodified_hotspot_example_on_several_slabs(tmp_path, monkeypatch):
+    """STST_DEVICES spreads the unmodified example's single `update(grid)` call
+    (examples/hotspot/hotspot.cpp:297-305) over row slabs; the output file must not change by a byte.
+    (One GPU listed twice exercises the same path on a one-GPU box.)"""
+    binary = _binary("hotspot")
+    case_dir = OUT / "cases" / "hotspot"
+    expected = case_dir / "expected"
+    if not expected.exists():
+        pytest.skip("expected outputs not generated")
+    monkeypatch.setenv("STST_DEVICES", "0,0,0")
+    B.run_case("hotspot", case_dir, binary, tmp_path / "out")
+    assert filecmp.cmp(tmp_path / "out" / "out.bin", expected / "out.bin", shallow=False)
