@@ -464,6 +464,12 @@ class Context:
         self.rank, self.world, self.device = rank, world, local_rank
         os.environ["STST_DEVICE"] = str(self.device)
         self.dist = None
+        self.placement = None
+        if world > 1 and os.environ.get("STST_BIND_NUMA", "1") != "0":
+            # every rank next to its GPU: host threads (and, by first touch, the pinned cell images)
+            # on the cores of the GPU's NUMA node
+            from stencilstream_b200.affinity import bind_to_gpu_numa_node
+            self.placement = bind_to_gpu_numa_node(self.device)
         if world > 1:
             import torch
             import torch.distributed as dist_mod
@@ -756,6 +762,7 @@ def measure(args, ctx: Context, cpu_seconds: float = 12.0, parity: bool = True):
         "parity": parity_record,
         "gpu_launches": int(launches),
         "clocks": clocks.summary(),
+        "host_placement": ctx.placement,
     }
 
 

@@ -22,8 +22,10 @@ host code uses):
                      -> `scaling.cuda.csv` with the reference's columns
                      grid_wh,n_iters,runtime,measured_throughput,model_throughput; sizes already
                      in the file are skipped (resumable, as in the reference).
-  ncu_metrics        the metric list of scripts/benchmark-common.jl:246-283, for use under
-                     `ncu --csv --metrics ...` (prints the command; profiling is a separate run).
+  ncu_metrics        ncu_profile_command of scripts/benchmark-common.jl:246-283: profiles one launch of
+                     the fused sweep kernel under ncu, scrapes the reference's ten figures (occupancy,
+                     SM/DRAM/L1/L2 throughput, DRAM read/write volume, sectors per request) and merges
+                     them into metrics.cuda.json (run it under gpurun; ncu replays the launch).
 
 Model. The reference models its cuda backend as one HBM read + one write of the grid per sweep at
 80 % of the A100's bandwidth, or 10 us of launch latency per sweep, whichever is larger
@@ -179,20 +181,101 @@ def deep_grid_scaling(args):
         first = False
 
 
-NCU_METRICS = [  # scripts/benchmark-common.jl:246-283
-    "sm__warps_active.avg.pct_of_peak_sustained_active", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
-    "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__throughput.avg.pct_of_peak_sustained_active",
-    "lts__throughput.avg.pct_of_peak_sustained_elapsed", "sm__maximum_warps_per_active_cycle_pct",
+# ---- ncu scraping (reference scripts/benchmark-common.jl:246-283) ----------------------------------------
+# The reference profiles its command twice (default sections, then MemoryWorkloadAnalysis_Tables with
+# --print-details all), picks one launch and stores ten figures next to the throughput numbers of
+# metrics.<variant>.json. Same figures here, from ONE profiled launch of the fused sweep kernel.
+
+NCU_SECTIONS = ["SpeedOfLight", "Occupancy", "MemoryWorkloadAnalysis_Tables"]
+NCU_RAW_METRICS = [
     "dram__bytes_read.sum", "dram__bytes_write.sum",
     "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum",
     "l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum", "l1tex__t_requests_pipe_lsu_mem_global_op_st.sum",
 ]
+_UNIT_SCALE = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+
+
+def ncu_command(workload, rows, cols, iterations, launch_skip=1):
+    cmd = ["ncu", "--csv", "--clock-control", "none", "-k", "regex:fused_sweep_kernel",
+           "-s", str(launch_skip), "-c", "1", "--print-details", "all"]
+    for section in NCU_SECTIONS:
+        cmd += ["--section", section]
+    cmd += ["--metrics", ",".join(NCU_RAW_METRICS)]
+    cmd += [sys.executable, str(ROOT / "scripts" / "run_one.py"), "--workload", workload, "--rows",
+            str(rows), "--cols", str(cols), "--iters", str(iterations), "--calls", "1"]
+    return cmd
+
+
+def parse_ncu_csv(text):
+    """Rows of ncu's --csv output as dictionaries; everything before the header line (the profiled
+    program's own output, ==PROF== lines, ==WARNING== lines) is skipped, like
+    extract_ncu_profiling_data does (benchmark-common.jl:222-244)."""
+    lines = [line for line in text.splitlines() if not line.startswith("==")]
+    start = next((i for i, line in enumerate(lines) if line.startswith('"ID"')), None)
+    if start is None:
+        raise ValueError("no ncu CSV header in the output")
+    return list(csv.DictReader(lines[start:]))
+
+
+def _number(row):
+    value = float(row["Metric Value"].replace(",", ""))
+    return value * _UNIT_SCALE.get(row["Metric Unit"], 1.0)
+
+
+def scrape_ncu_metrics(rows, launch_id=None):
+    """The ten figures of ncu_profile_command (benchmark-common.jl:246-283) for one launch."""
+    if launch_id is None:
+        launch_id = rows[0]["ID"]
+    mine = [r for r in rows if r["ID"] == str(launch_id)]
+
+    def metric(name):
+        for r in mine:
+            if r["Metric Name"] == name:
+                return _number(r)
+        raise KeyError(f"ncu output has no metric {name!r} for launch {launch_id}")
+
+    return {
+        "achieved_occupancy": metric("Achieved Occupancy"),
+        "compute_throughput": metric("Compute (SM) Throughput"),
+        "dram_throughput": metric("DRAM Throughput"),
+        "l1_throughput": metric("L1/TEX Cache Throughput"),
+        "l2_throughput": metric("L2 Cache Throughput"),
+        "theoretical_occupancy": metric("Theoretical Occupancy"),
+        "read_volume": metric("dram__bytes_read.sum"),
+        "write_volume": metric("dram__bytes_write.sum"),
+        "sectors_per_load_request": metric("l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum")
+        / max(metric("l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum"), 1.0),
+        "sectors_per_store_request": metric("l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum")
+        / max(metric("l1tex__t_requests_pipe_lsu_mem_global_op_st.sum"), 1.0),
+        "kernel": mine[0]["Kernel Name"] if mine else None,
+    }
 
 
 def ncu_metrics(args):
-    rows, cols = args.rows or 16384, args.cols or args.rows or 16384
-    print("ncu --csv --clock-control none -k regex:fused_sweep --metrics " + ",".join(NCU_METRICS) +
-          f" python scripts/run_one.py --workload {args.workload} --rows {rows} --cols {cols} --iters 24")
+    """Profile one full-depth launch of the workload under ncu and merge the reference's ten
+    profiling figures into <out-dir>/metrics.cuda.json (the file max_perf writes)."""
+    import subprocess
+
+    runner_info = Runner(args.workload).info
+    if args.workload == "fdtd":
+        from stencilstream_b200 import workloads as W
+        rows = cols = W.FdtdExperiment(W.FDTD_MAX_GRID).grid_wh()
+    else:
+        rows, cols = args.rows or 16384, args.cols or args.rows or 16384
+    cmd = ncu_command(args.workload, rows, cols, args.iterations or 48)
+    print("+ " + " ".join(cmd), file=sys.stderr)
+    proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    if proc.returncode != 0:
+        raise SystemExit(f"ncu failed ({proc.returncode}):\n{proc.stdout[-2000:]}\n{proc.stderr[-2000:]}")
+    (Path(args.out_dir) / f"ncu_{args.workload}.csv").write_text(proc.stdout)
+    figures = scrape_ncu_metrics(parse_ncu_csv(proc.stdout))
+    figures["grid"] = [rows, cols]
+    figures["cell_size"] = int(runner_info.cell_bytes)
+    out = Path(args.out_dir) / "metrics.cuda.json"
+    metrics = json.loads(out.read_text()) if out.exists() else {"target": TARGET_NAME[args.workload]}
+    metrics.update(figures)
+    out.write_text(json.dumps(metrics, indent=1))
+    print(json.dumps(figures))
 
 
 def main():

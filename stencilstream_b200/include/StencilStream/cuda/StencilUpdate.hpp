@@ -52,9 +52,13 @@ namespace stencil {
 namespace cuda {
 
 template <concepts::TransitionFunction F, bool split_cell_structure = false> class StencilUpdate {
-  private:
+  public:
+    // (public: nvcc's host-side rewriting of designated initialisers such as
+    // `{.halo_value = MyCell{}}` names the aggregate's member types through these aliases)
     using Cell = typename F::Cell;
     using TDV = typename F::TimeDependentValue;
+
+  private:
     using Layout = internal::CellLayout<Cell>;
 
     static_assert(std::is_trivially_copyable_v<F>,
@@ -217,6 +221,91 @@ template <concepts::TransitionFunction F, bool split_cell_structure = false> cla
             return false;
         static const bool enabled = internal::env_long("STST_SPECULATE", 1) != 0;
         return enabled;
+    }
+
+    /// Planes of fields the cell type declares constant (`Cell::constant_fields`, see
+    /// cuda/internal/Helpers.hpp), if using them pays (same rule as for detected ones).
+    static constexpr unsigned declared_constant = internal::constant_fields_mask<Cell>();
+    static_assert(declared_constant != ~0u || Layout::n_planes >= 32,
+                  "every entry of Cell::constant_fields must also be listed in Cell::fields");
+
+    static bool declared_passthrough_pays() {
+        if constexpr (declared_constant == 0 || !internal::speculation_capable<F>()) {
+            return false;
+        } else {
+            std::size_t bytes = 0;
+            for (std::size_t i = 0; i < Layout::n_planes; i++)
+                if ((declared_constant >> i) & 1u)
+                    bytes += Layout::plane_bytes(i);
+            return speculation_enabled() && 4 * bytes >= sizeof(Cell) && sizeof(Cell) <= 64;
+        }
+    }
+
+    /**
+     * The generation loop with DECLARED constant fields: the pass-through kernels with a keep mask
+     * known at compile time. No observing launch and no read-back — the call stays asynchronous.
+     * With STST_VERIFY_CONSTANT_FIELDS=1 the kernels' own check of the kept planes is read after the
+     * last launch (one stream synchronisation) and a violated declaration throws std::logic_error.
+     */
+    GridImpl run_declared(GridImpl &source_grid) {
+        using namespace internal;
+        auto &source = source_grid.get_storage();
+        const unsigned grid_h = unsigned(source.height), grid_w = unsigned(source.width);
+        source.require_device();
+        if (spec_flags && spec_device != source.device) {
+            device_free(spec_device, spec_flags, default_stream(spec_device));
+            spec_flags = nullptr;
+        }
+        const std::size_t flag_bytes = sizeof(unsigned) * (max_spec_subiterations + 1);
+        if (!spec_flags) {
+            spec_device = source.device;
+            spec_flags = static_cast<unsigned *>(device_alloc(spec_device, flag_bytes, source.stream));
+            STST_RT_CHECK(stst_memset_async(spec_flags, 0, flag_bytes, source.stream));
+        }
+        Speculation spec{};
+        for (unsigned q = 0; q < n_sub; q++)
+            spec.keep[q] = spec_keep[q] = declared_constant & all_planes;
+        spec.flags = spec_flags;
+        spec_probed = true;
+        const LaunchPlan plan =
+            make_plan<F>(source.device, grid_h, grid_w, params.n_iterations, params.fused_iterations,
+                         params.tile_rows, spec.single_planes(n_sub, all_planes));
+        last_plan = plan;
+        GridImpl swap_a = source_grid.make_similar();
+        GridImpl swap_b = (params.n_iterations > plan.fused_iterations) ? source_grid.make_similar()
+                                                                         : swap_a;
+        swap_a.get_storage().allocate_device();
+        swap_b.get_storage().allocate_device();
+        GridImpl *pass_source = &source_grid, *pass_target = &swap_a;
+        std::size_t iteration = params.iteration_offset, remaining = params.n_iterations;
+        bool first = true;
+        while (remaining > 0) {
+            const unsigned n_gens = unsigned(std::min<std::size_t>(remaining, plan.fused_iterations));
+            launch(plan, pass_source->get_storage(), pass_target->get_storage(), iteration, n_gens,
+                   &spec);
+            iteration += n_gens;
+            remaining -= n_gens;
+            if (first) {
+                pass_source = &swap_a;
+                pass_target = &swap_b;
+                first = false;
+            } else {
+                std::swap(pass_source, pass_target);
+            }
+        }
+        pass_source->get_storage().device_written();
+        static const bool verify = env_long("STST_VERIFY_CONSTANT_FIELDS", 0) != 0;
+        if (verify) {
+            unsigned host_flags[max_spec_subiterations + 1] = {};
+            STST_RT_CHECK(stst_memcpy_d2h_async(host_flags, spec_flags, flag_bytes, source.stream));
+            STST_RT_CHECK(stst_stream_synchronize(source.stream));
+            if (host_flags[max_spec_subiterations] != 0)
+                throw std::logic_error(
+                    "StencilStream-B200: the transition function changed a field that its cell type "
+                    "lists in Cell::constant_fields (plane mask " +
+                    std::to_string(host_flags[max_spec_subiterations]) + ")");
+        }
+        return *pass_source;
     }
 
     /**
@@ -395,7 +484,12 @@ template <concepts::TransitionFunction F, bool split_cell_structure = false> cla
                 shards.reset();
             }
         }
-        if constexpr (internal::speculation_capable<F>()) {
+        if constexpr (declared_constant != 0 && internal::speculation_capable<F>()) {
+            // fields declared constant by the cell type: no run-time detection on top of that
+            if (declared_passthrough_pays() && source_grid.get_grid_height() > 0 &&
+                source_grid.get_grid_width() > 0)
+                return run_declared(source_grid);
+        } else if constexpr (internal::speculation_capable<F>()) {
             if (speculation_enabled() && !speculation_has_nothing_left() &&
                 source_grid.get_grid_height() > 0 && source_grid.get_grid_width() > 0)
                 return run_speculative(source_grid);

@@ -124,6 +124,62 @@ template <typename Cell> struct CellLayout {
     }
 };
 
+/**
+ * Opt-in declaration of fields a cell's transition functions never change (B200 extension; the
+ * reference API has nothing like it — SURVEY.md H4):
+ *
+ *     struct HotspotCell { float temp, power;
+ *         static constexpr auto fields = std::make_tuple(&HotspotCell::temp, &HotspotCell::power);
+ *         static constexpr auto constant_fields = std::make_tuple(&HotspotCell::power); };
+ *
+ * The tile sweeps then leave those planes in place instead of copying them from tile buffer to tile
+ * buffer, and keep them in ONE tile buffer (taller tiles) — the same kernels that the run-time
+ * detection of such fields uses (speculative plane pass-through, StencilUpdate.hpp), but decided at
+ * compile time: no observing launch, no verification read-back, so `blocking = false` calls stay
+ * asynchronous. Every entry must also be listed in `Cell::fields`. It is a contract: a transition
+ * function that does change a declared field gets the old value back (the kernels still detect it;
+ * set STST_VERIFY_CONSTANT_FIELDS=1 to have updates check and throw).
+ */
+template <typename Cell>
+concept HasConstantFieldList = HasFieldList<Cell> && requires {
+    Cell::constant_fields;
+    requires(std::tuple_size_v<std::remove_cvref_t<decltype(Cell::constant_fields)>> >= 1);
+};
+
+namespace detail {
+template <typename A, typename B> constexpr bool same_member(A a, B b) {
+    if constexpr (std::is_same_v<A, B>)
+        return a == b;
+    else
+        return false;
+}
+
+template <typename Cell, typename MemberPtr> constexpr unsigned plane_bit_of(MemberPtr member) {
+    unsigned bit = 0, index = 0;
+    std::apply([&](auto... listed) { ((bit |= same_member(listed, member) ? (1u << index) : 0u, index++), ...); },
+               Cell::fields);
+    return bit;
+}
+} // namespace detail
+
+/// Bit i set: plane i holds a field listed in `Cell::constant_fields` (0 without such a list).
+template <typename Cell> constexpr unsigned constant_fields_mask() {
+    if constexpr (HasConstantFieldList<Cell> && CellLayout<Cell>::is_split) {
+        unsigned mask = 0;
+        bool all_listed = true;
+        std::apply(
+            [&](auto... constant) {
+                ((mask |= detail::plane_bit_of<Cell>(constant),
+                  all_listed = all_listed && detail::plane_bit_of<Cell>(constant) != 0),
+                 ...);
+            },
+            Cell::constant_fields);
+        return all_listed ? mask : ~0u; // ~0u: an entry that is not in Cell::fields (static_assert'ed)
+    } else {
+        return 0;
+    }
+}
+
 /// Invoke `f(std::integral_constant<size_t, I>{})` for every plane index of `Cell`.
 #if defined(__CUDACC__)
     #pragma nv_exec_check_disable

@@ -168,6 +168,19 @@ template <typename F> class SlabUpdate {
             peer_base[s] = nullptr;
             peer_row_lo[s] = peer_row_hi[s] = 0;
         }
+        // Fields the cell type declares constant (Cell::constant_fields, Helpers.hpp): the
+        // pass-through kernels with a compile-time keep mask; none of the backup / verify / repeat
+        // protocol of the run-time detection below is needed for them.
+        if constexpr (constant_fields_mask<Cell>() != 0 && speculation_capable<F>() &&
+                      sizeof(Cell) <= 64) {
+            if (env_long("STST_SPECULATE", 1) != 0) {
+                for (unsigned q = 0; q < n_sub; q++)
+                    spec_keep[q] = constant_fields_mask<Cell>() & all_planes;
+                spec_probed = true;
+                settle_speculation();
+                declared_active = current_spec().single_planes(n_sub, all_planes) != 0;
+            }
+        }
     }
 
     SlabUpdate(SlabUpdate const &) = delete;
@@ -198,6 +211,8 @@ template <typename F> class SlabUpdate {
     /// Turn pass-through on or off for the following run() calls (no-op for functors without a
     /// second plane). Returns whether it is on.
     bool enable_speculation(bool on) {
+        if (declared_active)
+            return false; // the constant fields are declared: nothing to detect, nothing to verify
         // (cells beyond 64 bytes never profit, see settle_speculation: do not even start the
         // protocol for them — its backup would be a third copy of a very large slab)
         if constexpr (speculation_capable<F>() && sizeof(Cell) <= 64)
@@ -208,6 +223,8 @@ template <typename F> class SlabUpdate {
 
     /// Planes that currently pass through every sub-iteration.
     unsigned passthrough_planes() const {
+        if (declared_active)
+            return current_spec().single_planes(n_sub, all_planes);
         if (!spec_enabled || !spec_probed)
             return 0;
         return current_spec().single_planes(n_sub, all_planes);
@@ -283,7 +300,8 @@ template <typename F> class SlabUpdate {
     LaunchPlan const &get_plan() const { return plan; }
     /// The plan the next pass will use (taller tiles once planes pass through).
     LaunchPlan const &get_active_plan() const {
-        return (spec_enabled && spec_probed && !spec_exhausted()) ? spec_plan : plan;
+        return (declared_active || (spec_enabled && spec_probed && !spec_exhausted())) ? spec_plan
+                                                                                        : plan;
     }
     Config const &get_config() const { return cfg; }
     std::size_t get_n_launches() const { return n_launches; }
@@ -513,7 +531,8 @@ template <typename F> class SlabUpdate {
                 observe.flags = spec_flags;
                 pass(tf, halo_value, iteration, n_gens, &observe);
                 read_observation();
-            } else if (speculation_active()) {
+            } else if (speculation_active() || declared_active) {
+                ensure_spec_flags();
                 const Speculation spec = current_spec();
                 pass(tf, halo_value, iteration, n_gens, &spec);
             } else {
@@ -822,6 +841,7 @@ template <typename F> class SlabUpdate {
     std::unique_ptr<Event> boundary_done, interior_done;
     // speculative plane pass-through
     bool spec_enabled = false, spec_probed = false;
+    bool declared_active = false; ///< keep masks come from Cell::constant_fields
     unsigned spec_keep[max_spec_subiterations] = {};
     unsigned *spec_flags = nullptr;
     LaunchPlan spec_plan{};

@@ -112,3 +112,46 @@ def test_bench_parity_window_agrees_with_a_whole_grid_oracle_run(oracle_best):
         field[64, 64] *= 1.001
         bad = bench.check_parity_window(workload, params, halo, fill, rows, cols, iters, 0, rows, broken)
         assert not bad["ok"] and bad["rel_max_norm"] > 1e-5
+
+
+NCU_CSV = '''==PROF== Connected to process 4242 (/usr/bin/python3.12)
+jacobi5 k=6 tile=43x240 call 0: 7.5 ms
+==PROF== Profiling "fused_sweep_kernel" - 0: 0%....50%....100% - 9 passes
+==PROF== Disconnected from process 4242
+"ID","Process ID","Process Name","Host Name","Kernel Name","Context","Stream","Block Size","Grid Size","Device","CC","Section Name","Metric Name","Metric Unit","Metric Value"
+"0","4242","python3.12","127.0.0.1","void fused_sweep_kernel<Jacobi5Rule, 4, 1, 64, 256, 1, 0>(...)","1","7","(64, 4, 1)","(26358, 1, 1)","0","10.0","Command line profiler metrics","dram__bytes_read.sum","Gbyte","1.07"
+"0","4242","python3.12","127.0.0.1","void fused_sweep_kernel<Jacobi5Rule, 4, 1, 64, 256, 1, 0>(...)","1","7","(64, 4, 1)","(26358, 1, 1)","0","10.0","Command line profiler metrics","dram__bytes_write.sum","Gbyte","1.03"
+"0","4242","python3.12","127.0.0.1","void fused_sweep_kernel<Jacobi5Rule, 4, 1, 64, 256, 1, 0>(...)","1","7","(64, 4, 1)","(26358, 1, 1)","0","10.0","Command line profiler metrics","l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum","sector","0"
+"0","4242","python3.12","127.0.0.1","void fused_sweep_kernel<Jacobi5Rule, 4, 1, 64, 256, 1, 0>(...)","1","7","(64, 4, 1)","(26358, 1, 1)","0","10.0","Command line profiler metrics","l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum","","0"
+"0","4242","python3.12","127.0.0.1","void fused_sweep_kernel<Jacobi5Rule, 4, 1, 64, 256, 1, 0>(...)","1","7","(64, 4, 1)","(26358, 1, 1)","0","10.0","Command line profiler metrics","l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum","sector","33,554,432"
+"0","4242","python3.12","127.0.0.1","void fused_sweep_kernel<Jacobi5Rule, 4, 1, 64, 256, 1, 0>(...)","1","7","(64, 4, 1)","(26358, 1, 1)","0","10.0","Command line profiler metrics","l1tex__t_requests_pipe_lsu_mem_global_op_st.sum","","2,097,152"
+"0","4242","python3.12","127.0.0.1","void fused_sweep_kernel<Jacobi5Rule, 4, 1, 64, 256, 1, 0>(...)","1","7","(64, 4, 1)","(26358, 1, 1)","0","10.0","GPU Speed Of Light Throughput","DRAM Throughput","%","27.6"
+"0","4242","python3.12","127.0.0.1","void fused_sweep_kernel<Jacobi5Rule, 4, 1, 64, 256, 1, 0>(...)","1","7","(64, 4, 1)","(26358, 1, 1)","0","10.0","GPU Speed Of Light Throughput","L1/TEX Cache Throughput","%","71.2"
+"0","4242","python3.12","127.0.0.1","void fused_sweep_kernel<Jacobi5Rule, 4, 1, 64, 256, 1, 0>(...)","1","7","(64, 4, 1)","(26358, 1, 1)","0","10.0","GPU Speed Of Light Throughput","L2 Cache Throughput","%","12.9"
+"0","4242","python3.12","127.0.0.1","void fused_sweep_kernel<Jacobi5Rule, 4, 1, 64, 256, 1, 0>(...)","1","7","(64, 4, 1)","(26358, 1, 1)","0","10.0","GPU Speed Of Light Throughput","Compute (SM) Throughput","%","64.5"
+"0","4242","python3.12","127.0.0.1","void fused_sweep_kernel<Jacobi5Rule, 4, 1, 64, 256, 1, 0>(...)","1","7","(64, 4, 1)","(26358, 1, 1)","0","10.0","Occupancy","Theoretical Occupancy","%","25"
+"0","4242","python3.12","127.0.0.1","void fused_sweep_kernel<Jacobi5Rule, 4, 1, 64, 256, 1, 0>(...)","1","7","(64, 4, 1)","(26358, 1, 1)","0","10.0","Occupancy","Achieved Occupancy","%","24.4"
+'''
+
+
+def test_ncu_scraper_extracts_the_reference_figures():
+    """scripts/benchmark.py ncu_metrics: the ten figures of the reference's ncu_profile_command
+    (scripts/benchmark-common.jl:246-283) out of ncu's CSV, with the profiled program's own output and
+    the ==PROF== lines in front of it."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("benchmark_driver", ROOT / "scripts" / "benchmark.py")
+    driver = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(driver)
+    rows = driver.parse_ncu_csv(NCU_CSV)
+    assert len(rows) == 12 and rows[0]["Metric Name"] == "dram__bytes_read.sum"
+    figures = driver.scrape_ncu_metrics(rows)
+    assert abs(figures["read_volume"] - 1.07e9) < 1 and abs(figures["write_volume"] - 1.03e9) < 1
+    assert figures["achieved_occupancy"] == 24.4 and figures["theoretical_occupancy"] == 25
+    assert figures["compute_throughput"] == 64.5 and figures["dram_throughput"] == 27.6
+    assert figures["l1_throughput"] == 71.2 and figures["l2_throughput"] == 12.9
+    assert figures["sectors_per_store_request"] == 16.0 and figures["sectors_per_load_request"] == 0.0
+    cmd = driver.ncu_command("hotspot", 16384, 16384, 48)
+    assert cmd[0] == "ncu" and "--csv" in cmd and "regex:fused_sweep_kernel" in cmd
+    assert set(figures) >= {"achieved_occupancy", "compute_throughput", "dram_throughput", "l1_throughput",
+                            "l2_throughput", "theoretical_occupancy", "read_volume", "write_volume",
+                            "sectors_per_load_request", "sectors_per_store_request"}

@@ -104,3 +104,23 @@ def test_cuda_device_must_match_the_grid():
                                              n_iterations=2, cuda_device=7))
     with pytest.raises(ValueError):
         update(Grid("jacobi5", buffer=cells))
+
+
+@pytest.mark.parametrize("workload,shape,n,fused", [("hotspot", (331, 700), 9, 3),
+                                                    ("kat", (203, 260), 6, 2),
+                                                    ("jacobi_r3", (257, 520), 5, 2)])
+def test_sharded_call_with_cp_async_staging(monkeypatch, workload, shape, n, fused, oracle_best):
+    """STST_TMA=0: tiles are staged with cp.async / plain loads, which — unlike a TMA box, whose
+    tensor map ends with the slab — must not read rows beyond the slab's planes when the last tile row
+    of a launch overshoots the row range (the tile height does not divide it)."""
+    monkeypatch.setenv("STST_TMA", "0")
+    params, halo, cells = cases.make_case(workload, *shape, seed=17)
+    if "kat" in workload:
+        cells = cases.kat_input(*shape, 0)
+    update = StencilUpdate(workload, Params(transition_function=params, halo_value=halo,
+                                            n_iterations=n, blocking=True, fused_iterations=fused,
+                                            cuda_devices=device_list(3)), strict=True)
+    out = update(Grid(workload, buffer=cells, strict=True))
+    stats = update.get_stats()
+    assert stats.n_slabs == 3 and stats.use_tma == 0
+    assert out.to_numpy().tobytes() == oracle_best.run(workload, params, halo, cells, 0, n).tobytes()

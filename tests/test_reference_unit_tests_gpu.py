@@ -36,3 +36,15 @@ def test_own_cpp_tests_of_the_grid_extensions_pass():
     print(proc.stdout)
     assert proc.returncode == 0, proc.stdout + proc.stderr
     assert sum(line.startswith("[ OK ]") for line in proc.stdout.splitlines()) == 4
+
+
+def test_own_cpp_tests_of_the_update_extensions_pass():
+    """tests/cpp/update_extensions.cu: stencil radii beyond the column group, Cell::constant_fields,
+    Params::cuda_devices — through the C++ template API, against a host restatement of the sweep."""
+    binary = BINARY.parent.parent / "own_tests" / "unit_test_update_extensions_b200"
+    if not binary.exists():
+        pytest.skip(f"{binary} not built")
+    proc = subprocess.run([str(binary)], capture_output=True, text=True, timeout=600)
+    print(proc.stdout)
+    assert proc.returncode == 0, proc.stdout + proc.stderr
+    assert sum(line.startswith("[ OK ]") for line in proc.stdout.splitlines()) == 5
