@@ -278,6 +278,11 @@ int stst_slab_get_ipc_handle(stst_slab *slab, unsigned char handle[64]);
 int stst_slab_attach_ipc(stst_slab *slab, int side, const unsigned char handle[64],
                          size_t peer_row_lo, size_t peer_row_hi);
 int stst_slab_attach_local(stst_slab *slab, int side, stst_slab *peer);
+/* Alternative halo transport: grouped ncclSend/ncclRecv per pass instead of stores into mapped
+ * neighbour memory (no attach needed). nccl_comm: a communicator from stst_nccl_comm_init_rank
+ * (include/stst_rt.h) that spans the slabs' processes; up_rank/down_rank: the neighbours' ranks in it,
+ * negative where the slab has no neighbour. Every slab of a grid must use the same transport. */
+int stst_slab_use_nccl(stst_slab *slab, void *nccl_comm, int up_rank, int down_rank);
 /* Wait for the slab's work, then forget both neighbours and unmap their memory. Every slab of a grid
  * detaches before any of them is destroyed (a neighbour may still be pushing halo rows into it). */
 int stst_slab_detach(stst_slab *slab);

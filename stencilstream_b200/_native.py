@@ -193,7 +193,7 @@ WORKLOADS_SYMBOLS = [
     "stst_update_create",
     "stst_update_set_params", "stst_update_apply", "stst_update_get_stats", "stst_update_destroy",
     "stst_slab_create", "stst_slab_destroy", "stst_slab_get_info", "stst_slab_get_ipc_handle",
-    "stst_slab_attach_ipc", "stst_slab_attach_local", "stst_slab_detach", "stst_slab_copy_from_host",
+    "stst_slab_attach_ipc", "stst_slab_attach_local", "stst_slab_detach", "stst_slab_use_nccl", "stst_slab_copy_from_host",
     "stst_slab_copy_to_host", "stst_slab_copy_rows_from_host", "stst_slab_copy_rows_to_host",
     "stst_slab_exchange_halos", "stst_slab_update", "stst_slab_synchronize",
     "stst_slab_record_event",
@@ -216,6 +216,10 @@ def runtime_lib():
         lib.stst_last_error.restype = C.c_char_p
         lib.stst_get_device_info.argtypes = [C.c_int, C.POINTER(DeviceInfo)]
         lib.stst_device_count.argtypes = [C.POINTER(C.c_int)]
+        lib.stst_set_device.argtypes = [C.c_int]
+        lib.stst_nccl_get_unique_id.argtypes = [C.c_char_p]
+        lib.stst_nccl_comm_init_rank.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_char_p, C.c_int]
+        lib.stst_nccl_comm_destroy.argtypes = [C.c_void_p]
         _libs["rt"] = lib
     return _libs["rt"]
 

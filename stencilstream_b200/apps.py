@@ -19,7 +19,7 @@ libstst_workloads.so; this module only sequences calls, as the reference's `main
 from __future__ import annotations
 
 from dataclasses import dataclass, field
-from typing import Callable
+from typing import Any, Callable
 
 import numpy as np
 
@@ -177,3 +177,38 @@ def run_fdtd(config: dict, *, n_timesteps: int | None = None, n_snap_timesteps: 
     if on_frame is not None:
         on_frame("hz_sum", total, grid.field_to_numpy("hz_sum"))
     return grid, simulation
+
+
+def run_fdtd_sharded(config: dict, *, rank: int, world: int, device: int = 0, comm: Any = None,
+                     n_timesteps: int | None = None, n_snap_timesteps: int | None = None,
+                     strict: bool | None = None, fused_iterations: int = 0,
+                     slab_factory: Callable[..., Any] | None = None, transport: str | None = None,
+                     on_frame: Callable[[str, int, int, int, np.ndarray], None] | None = None):
+    """`run_fdtd` on row slabs, one process per GPU (reference examples/fdtd/src/fdtd.cpp:218-252: the
+    snapshot loop advances `iteration_offset` in steps of `n_snap_timesteps` and overshoots
+    `n_timesteps` to the next multiple). `on_frame(field, iteration, row_lo, row_hi, values)` receives
+    THIS rank's rows of `hz` after every interval and of `hz_sum` at the end — single-plane downloads,
+    4 of the 32 bytes of a cell. Collective. Returns the ShardedStencilUpdate holding the final cells."""
+    exp = W.FdtdExperiment(config)
+    total = exp.n_timesteps() if n_timesteps is None else int(n_timesteps)
+    snap = exp.n_snap_timesteps() if n_snap_timesteps is None else int(n_snap_timesteps)
+    wh = exp.grid_wh()
+    simulation = ShardedStencilUpdate(
+        "fdtd", Params(transition_function=exp.kernel_params(), halo_value=None, iteration_offset=0,
+                       n_iterations=snap or total, blocking=True, fused_iterations=fused_iterations),
+        wh, wh, rank=rank, world=world, device=device, comm=comm, strict=strict,
+        slab_factory=slab_factory, transport=transport)
+    lo, hi = simulation.row_lo, simulation.row_hi
+    simulation.load(exp.initial_grid()[lo:hi])
+    params = simulation.get_params()
+    if snap:
+        while params.iteration_offset < total:
+            simulation()
+            if on_frame is not None:
+                on_frame("hz", params.iteration_offset + snap, lo, hi, simulation.field_to_numpy("hz"))
+            params.iteration_offset += snap
+    else:
+        simulation()
+    if on_frame is not None:
+        on_frame("hz_sum", total, lo, hi, simulation.field_to_numpy("hz_sum"))
+    return simulation

@@ -346,6 +346,15 @@ STST_EXPORT int stst_slab_attach_local(stst_slab *slab, int side, stst_slab *pee
     });
 }
 
+STST_EXPORT int stst_slab_use_nccl(stst_slab *slab, void *nccl_comm, int up_rank, int down_rank) {
+    if (!slab || !nccl_comm)
+        return report(STST_ERR_INVALID_ARGUMENT, "null argument");
+    return guarded([&] {
+        slab->impl->use_nccl(nccl_comm, up_rank, down_rank);
+        return STST_OK;
+    });
+}
+
 STST_EXPORT int stst_slab_detach(stst_slab *slab) {
     if (!slab)
         return report(STST_ERR_INVALID_ARGUMENT, "null argument");

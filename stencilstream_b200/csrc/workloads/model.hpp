@@ -183,6 +183,7 @@ struct SlabBase {
     virtual int device() const = 0;
     virtual void attach(int side, void *mapped, std::size_t lo, std::size_t hi) = 0;
     virtual void detach() = 0;
+    virtual void use_nccl(void *comm, int up_rank, int down_rank) = 0;
     virtual void upload(const void *cells, std::size_t first_row, std::size_t n_rows) = 0;
     virtual void download(void *cells, std::size_t first_row, std::size_t n_rows) = 0;
     virtual void exchange() = 0;
@@ -246,6 +247,9 @@ template <typename F, typename ParamBlock> struct SlabHolder final : SlabBase {
     void attach(int side, void *mapped, std::size_t lo, std::size_t hi) override {
         slab->attach(side == 0 ? sc::internal::SlabSide::up : sc::internal::SlabSide::down, mapped,
                      lo, hi);
+    }
+    void use_nccl(void *comm, int up_rank, int down_rank) override {
+        slab->use_nccl(comm, up_rank, down_rank);
     }
     void detach() override {
         slab->detach();

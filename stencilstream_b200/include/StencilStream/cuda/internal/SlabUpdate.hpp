@@ -321,6 +321,24 @@ template <typename F> class SlabUpdate {
         peer_row_hi[s] = row_hi;
     }
 
+    /**
+     * Use NCCL instead of peer-mapped memory as the halo transport (north_star: "by P2P copies or NCCL
+     * send/recv"): after its boundary strips a pass sends them with one grouped ncclSend/ncclRecv
+     * exchange (stst_nccl_neighbor_exchange) and receives the neighbours' strips into its ghost rows.
+     * The exchange itself orders the slabs — no flags, no mapped neighbour memory, no attach(). It is
+     * the portable route (works wherever NCCL does, across nodes too); the default route stores
+     * straight into the neighbour while sweeping and needs no extra launch. `up_rank` / `down_rank`:
+     * NCCL ranks of the neighbours, negative where there is none. The communicator stays owned by the
+     * caller.
+     */
+    void use_nccl(stst_nccl_comm_t comm, int up_rank, int down_rank) {
+        if ((has_up() && up_rank < 0) || (has_down() && down_rank < 0))
+            throw std::invalid_argument("StencilStream-B200: a neighbouring slab has no NCCL rank");
+        nccl_comm = comm;
+        nccl_rank[0] = up_rank;
+        nccl_rank[1] = down_rank;
+    }
+
     /// Forget both neighbours (after waiting for this slab's work): nothing this slab does afterwards
     /// touches their memory, so their owners may free it. Every slab of a grid detaches before any
     /// of them is destroyed (sharding.py: barrier, detach, barrier, destroy).
@@ -492,6 +510,11 @@ template <typename F> class SlabUpdate {
         epoch += 2;
         const int cur = int(epoch & 1);
         const PlaneSet mine = layout.planes(base, cur);
+        if (nccl_comm) {
+            nccl_exchange(cur);
+            fork_streams();
+            return;
+        }
         for (int s = 0; s < 2; s++) {
             if (!has_side(s))
                 continue;
@@ -692,7 +715,7 @@ template <typename F> class SlabUpdate {
         HaloPush push{};
         push.up_row_hi = INT_MIN;
         push.down_row_lo = INT_MAX;
-        for (int s = 0; s < 2; s++) {
+        for (int s = 0; s < 2 && !nccl_comm; s++) {
             if (!has_side(s))
                 continue;
             require_attached(s);
@@ -708,7 +731,8 @@ template <typename F> class SlabUpdate {
                 push.down_row_lo = int(cfg.row_hi - ghost);
             }
         }
-        const bool pushes = has_up() || has_down();
+        const bool neighbours = has_up() || has_down();
+        const bool pushes = neighbours && !nccl_comm; // store into mapped neighbour memory + flags
 
         LaunchRegion region{};
         region.device = cfg.device;
@@ -719,7 +743,7 @@ template <typename F> class SlabUpdate {
 
         // Everything launched in this pass reads rows written by BOTH streams in the previous pass.
         join_streams();
-        for (int s = 0; s < 2; s++) {
+        for (int s = 0; s < 2 && !nccl_comm; s++) {
             if (has_side(s))
                 STST_RT_CHECK(stst_stream_wait_value32_geq(boundary_stream, my_flag(s),
                                                            unsigned(epoch + 1)));
@@ -753,7 +777,7 @@ template <typename F> class SlabUpdate {
             n_launches++;
         };
 
-        const bool split = cfg.overlap && pushes && owned_rows() > 2 * ghost;
+        const bool split = cfg.overlap && neighbours && owned_rows() > 2 * ghost;
         if (split) {
             // Two launches per pass: both boundary strips (with the halo push and the flags), then
             // the interior. (Until round 2 this was five: a launch per strip and a one-thread kernel
@@ -762,11 +786,43 @@ template <typename F> class SlabUpdate {
             const std::size_t top_hi = has_up() ? cfg.row_lo + ghost : cfg.row_lo;
             const std::size_t bottom_lo = has_down() ? cfg.row_hi - ghost : cfg.row_hi;
             sweep(cfg.row_lo, top_hi, bottom_lo, cfg.row_hi, true, true, boundary_stream);
+            if (nccl_comm)
+                nccl_exchange(cur ^ 1); // strips out, ghost rows of the next generation in
             sweep(top_hi, bottom_lo, 0, 0, false, false, interior_stream);
         } else {
             sweep(cfg.row_lo, cfg.row_hi, 0, 0, true, false, boundary_stream);
+            if (nccl_comm)
+                nccl_exchange(cur ^ 1);
         }
         epoch++;
+    }
+
+    /// Send the `ghost` owned rows next to each neighbour, receive that neighbour's into the ghost
+    /// rows on the same side — all planes, both sides, one NCCL group on the boundary stream.
+    void nccl_exchange(int buffer) {
+        const PlaneSet mine = layout.planes(base, buffer);
+        int peers[2 * max_planes];
+        const void *send[2 * max_planes];
+        void *recv[2 * max_planes];
+        std::size_t send_bytes[2 * max_planes], recv_bytes[2 * max_planes];
+        int n = 0;
+        for (int s = 0; s < 2; s++) {
+            if (!has_side(s))
+                continue;
+            const std::size_t my_first = (s == 0) ? ghost : owned_rows();        // rows I own there
+            const std::size_t ghost_first = (s == 0) ? 0 : ghost + owned_rows(); // rows I receive
+            for (std::size_t i = 0; i < Layout::n_planes; i++, n++) {
+                const std::size_t row_bytes = layout.pitch[i] * Layout::plane_bytes(i);
+                unsigned char *plane = static_cast<unsigned char *>(mine.base[i]);
+                peers[n] = nccl_rank[s];
+                send[n] = plane + my_first * row_bytes;
+                recv[n] = plane + ghost_first * row_bytes;
+                send_bytes[n] = recv_bytes[n] = ghost * row_bytes;
+            }
+        }
+        if (n > 0)
+            STST_RT_CHECK(stst_nccl_neighbor_exchange(nccl_comm, n, peers, send, send_bytes, recv,
+                                                      recv_bytes, boundary_stream));
     }
 
     void check_row_range(std::size_t first_row, std::size_t n_rows) const {
@@ -842,6 +898,9 @@ template <typename F> class SlabUpdate {
     // speculative plane pass-through
     bool spec_enabled = false, spec_probed = false;
     bool declared_active = false; ///< keep masks come from Cell::constant_fields
+    // NCCL halo transport (use_nccl); nullptr: peer-mapped memory and flags
+    stst_nccl_comm_t nccl_comm = nullptr;
+    int nccl_rank[2] = {-1, -1};
     unsigned spec_keep[max_spec_subiterations] = {};
     unsigned *spec_flags = nullptr;
     LaunchPlan spec_plan{};

@@ -57,6 +57,7 @@ def _slab_lib(strict: bool | None = None):
         lib.stst_slab_attach_ipc.argtypes = [vp, C.c_int, C.c_char_p, C.c_size_t, C.c_size_t]
         lib.stst_slab_attach_local.argtypes = [vp, C.c_int, vp]
         lib.stst_slab_detach.argtypes = [vp]
+        lib.stst_slab_use_nccl.argtypes = [vp, vp, C.c_int, C.c_int]
         lib.stst_slab_copy_from_host.argtypes = [vp, vp, C.c_size_t]
         lib.stst_slab_copy_to_host.argtypes = [vp, vp, C.c_size_t]
         lib.stst_slab_copy_rows_from_host.argtypes = [vp, C.c_size_t, C.c_size_t, vp, C.c_size_t]
@@ -118,6 +119,10 @@ class NativeSlab:
 
     def attach_local(self, side: int, peer: "NativeSlab") -> None:
         _check(self._lib, self._lib.stst_slab_attach_local(self._handle, side, peer._handle))
+
+    def use_nccl(self, comm, up_rank: int, down_rank: int) -> None:
+        """Halo transport through the NCCL communicator `comm` (see stst_slab_use_nccl)."""
+        _check(self._lib, self._lib.stst_slab_use_nccl(self._handle, comm, up_rank, down_rank))
 
     def detach(self) -> None:
         """Wait for this slab, then forget and unmap both neighbours."""
@@ -217,7 +222,7 @@ class ShardedStencilUpdate:
     def __init__(self, workload: str, params: Params, grid_rows: int, grid_cols: int, *, rank: int,
                  world: int, device: int = 0, comm: Any = None, overlap: bool = True,
                  strict: bool | None = None, speculate: bool = True,
-                 slab_factory: Callable[..., Any] | None = None):
+                 slab_factory: Callable[..., Any] | None = None, transport: str | None = None):
         if world > 1 and comm is None:
             raise ValueError("a process group is needed to exchange slab handles")
         self.workload, self.params = workload, params
@@ -247,10 +252,31 @@ class ShardedStencilUpdate:
             comm.all_gather_object(everyone, mine)
             if len({e[3] for e in everyone}) != 1:
                 raise StencilStreamError("slabs disagree on the fusion depth")
-            for side, other in ((0, rank - 1), (1, rank + 1)):
-                if 0 <= other < world:
-                    handle, lo, hi, _ = everyone[other]
-                    self.slab.attach_ipc(side, handle, lo, hi)
+            import os
+            self.transport = transport or os.environ.get("STST_HALO_TRANSPORT", "p2p")
+            if self.transport == "nccl":
+                # the portable route: one grouped ncclSend/ncclRecv exchange per pass, through a
+                # communicator of the runtime's own (include/stst_rt.h); rank 0's id reaches the others
+                # through the process group
+                rt = _native.runtime_lib()
+                uid = C.create_string_buffer(128)
+                if rank == 0 and rt.stst_nccl_get_unique_id(uid) != 0:
+                    raise StencilStreamError(rt.stst_last_error().decode())
+                ids = [None] * world
+                comm.all_gather_object(ids, uid.raw)
+                rt.stst_set_device(device)
+                self._nccl = C.c_void_p()
+                if rt.stst_nccl_comm_init_rank(C.byref(self._nccl), world, ids[0], rank) != 0:
+                    raise StencilStreamError(rt.stst_last_error().decode())
+                self.slab.use_nccl(self._nccl, rank - 1 if rank > 0 else -1,
+                                   rank + 1 if rank + 1 < world else -1)
+            elif self.transport == "p2p":
+                for side, other in ((0, rank - 1), (1, rank + 1)):
+                    if 0 <= other < world:
+                        handle, lo, hi, _ = everyone[other]
+                        self.slab.attach_ipc(side, handle, lo, hi)
+            else:
+                raise ValueError(f"unknown halo transport {self.transport!r} (p2p or nccl)")
         self._keepalive = None
         # plane pass-through: every slab must agree on whether the protocol runs at all
         wants = bool(speculate) and hasattr(self.slab, "enable_speculation") and \
@@ -416,3 +442,6 @@ class ShardedStencilUpdate:
             self._comm.barrier()
         self.slab.close()
         self.slab = None
+        if getattr(self, "_nccl", None):
+            _native.runtime_lib().stst_nccl_comm_destroy(self._nccl)
+            self._nccl = None

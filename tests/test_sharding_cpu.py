@@ -67,7 +67,8 @@ def _worker(rank, world, port, workload, shape, offset, n, depth, failures, mode
             count = C.c_int(0)
             _native.runtime_lib().stst_device_count(C.byref(count))
             extra = dict(device=rank % max(count.value, 1), strict=True,
-                         overlap=(mode != "cuda-no-overlap"))
+                         overlap=(mode != "cuda-no-overlap"),
+                         transport="nccl" if mode == "cuda-nccl" else "p2p")
         update = ShardedStencilUpdate(
             workload, Params(transition_function=params, halo_value=halo, iteration_offset=offset,
                              n_iterations=n, blocking=True, fused_iterations=depth),

@@ -34,3 +34,26 @@ def test_wrong_passthrough_guess_is_repeated_on_every_slab(world, built):
     generation and repeat the call. `redo_expected` makes the workers assert that this happened and
     that the material coefficients still pass through afterwards."""
     run_group(world, "fdtd", (150, 333), 0, 14, 2, "cuda-redo_expected")
+
+
+def _device_count():
+    import ctypes as C
+    from stencilstream_b200 import _native
+    count = C.c_int(0)
+    _native.runtime_lib().stst_device_count(C.byref(count))
+    return count.value
+
+
+@pytest.mark.parametrize("workload,shape,offset,n,depth", [
+    ("hotspot", (330, 700), 0, 7, 3),
+    ("fdtd", (150, 333), 3, 4, 2),
+    ("jacobi5", (1000, 1030), 0, 20, 4),
+])
+def test_nccl_halo_transport_equals_whole_grid(workload, shape, offset, n, depth, built):
+    """The portable halo route: one grouped ncclSend/ncclRecv exchange per pass through the runtime's
+    own communicator (stst_nccl_comm_init_rank / stst_nccl_neighbor_exchange, include/stst_rt.h)
+    instead of stores into IPC-mapped neighbour memory. NCCL refuses two ranks on one device, so this
+    needs a box with at least two GPUs."""
+    if _device_count() < 2:
+        pytest.skip("NCCL needs one GPU per rank")
+    run_group(2, workload, shape, offset, n, depth, "cuda-nccl")
