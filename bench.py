@@ -348,7 +348,15 @@ def check_parity_window(workload, params, halo, fill, total_rows, cols, iters, r
         return {"window": [[w0, w1], [c0, c1]], "rel_max_norm": None,
                 "skipped": f"domain of dependence {r1 - r0}x{k1 - k0} x {iters} iterations exceeds the "
                            "bench's CPU budget; covered by tests/test_parity_fullsize_gpu.py"}
-    checker = oracle.best()
+    # The oracle whose arithmetic matches the build under test: the default build contracts a*b+c into
+    # FMAs (as the reference's own icpx build does), so its checker is the reference cpu backend
+    # compiled with contraction allowed; STST_STRICT=1 (-fmad=false) is checked against the
+    # uncontracted build. The other flavour is reported beside it (`rel_max_norm_vs_*`).
+    strict_build = os.environ.get("STST_STRICT", "0") not in ("", "0")
+    contracted = None if strict_build else (oracle.reference(fma=True) or
+                                            (oracle.port(fma=True) if oracle.cpu_has_fma() else None))
+    checker = contracted or oracle.best()
+    other = oracle.best() if contracted is not None else None
     cores = oracle.set_threads()
     band = np.empty((r1 - r0, cols), dtype=cells.dtype)
     fill(band, r0, r1, total_rows)
@@ -359,20 +367,38 @@ def check_parity_window(workload, params, halo, fill, total_rows, cols, iters, r
     seconds = time.perf_counter() - t0
     want = want[w0 - r0:w1 - r0, c0 - k0:c1 - k0]
     got = np.ascontiguousarray(cells[w0 - row_lo:w1 - row_lo, c0:c1])
-    if workload == "conway":
-        err = 0.0 if got.tobytes() == want.tobytes() else 1.0
-        bar = 0.0
-    else:
-        err, bar = 0.0, PARITY_TOLERANCE
+
+    def distance(want):
+        if workload == "conway":
+            return 0.0 if got.tobytes() == want.tobytes() else 1.0
+        err = 0.0
         for name in (got.dtype.names or (None,)):
             a = (got[name] if name else got).astype(np.float64)
             b = (want[name] if name else want).astype(np.float64)
             scale = np.abs(b).max()
             err = max(err, float(np.abs(a - b).max() / scale) if scale > 0 else float(np.abs(a).max()))
+        return err
+
+    err = distance(want)
+    bar = 0.0 if workload == "conway" else PARITY_TOLERANCE
+    extra = {}
+    if other is not None and workload != "conway":
+        want_other = other.run_window2d(workload, params, halo, crop, r0, k0, total_rows, cols, 0, iters)
+        extra = {"rel_max_norm_vs_uncontracted_oracle":
+                     distance(want_other[w0 - r0:w1 - r0, c0 - k0:c1 - k0]),
+                 "note": "the default build contracts a*b+c into FMAs like the reference's icpx build; "
+                         "against the uncontracted oracle it drifts linearly with the iteration count "
+                         "(DESIGN.md section 5); STST_STRICT=1 selects the -fmad=false build, which is "
+                         "bit-exact against that oracle"}
     return {"window": [[w0, w1], [c0, c1]], "rel_max_norm": err, "tolerance": bar, "ok": err <= bar,
+            "bit_exact": bool(got.tobytes() == want.tobytes()),
             "iterations": iters, "oracle": checker.kind,
+            "oracle_arithmetic": "g++ -ffp-contract=fast -mfma (contracting, matches -fmad=true)"
+            if getattr(checker, "contracts", False) else "g++ -ffp-contract=off (matches -fmad=false)",
+            **extra,
             "domain_of_dependence": [r1 - r0, k1 - k0], "oracle_seconds": round(seconds, 2),
-            "oracle_threads": cores, "build": "default (FMA contraction on), the planner's plan"}
+            "oracle_threads": cores,
+            "build": ("-fmad=false" if strict_build else "default (-fmad=true)") + ", the planner's plan"}
 
 
 def workload_config(workload, total_rows, rows, cols, iters, world):

@@ -83,11 +83,17 @@ def test_bench_roofline_traffic_comes_from_the_committed_capture():
         assert (ROOT / entry["source"]).exists(), entry
 
 
-def test_bench_parity_window_agrees_with_a_whole_grid_oracle_run(oracle_best):
+def test_bench_parity_window_agrees_with_a_whole_grid_oracle_run(oracle_best, monkeypatch):
     """bench.py's `parity` record: the window check it runs after the end-to-end steps must report
-    zero for the oracle's own whole-grid result and a clear failure for a perturbed one."""
+    zero for the oracle's own whole-grid result and a clear failure for a perturbed one. (The result
+    handed in here is the UNcontracted oracle's, i.e. what the -fmad=false build produces: with
+    STST_STRICT=1 that oracle is the checker; without, it is the one reported beside the contracted
+    checker.)"""
     import numpy as np
     import bench
+    import oracle
+
+    monkeypatch.setenv("STST_STRICT", "1")
 
     rows = cols = 256
     iters = 12
@@ -112,6 +118,12 @@ def test_bench_parity_window_agrees_with_a_whole_grid_oracle_run(oracle_best):
         field[64, 64] *= 1.001
         bad = bench.check_parity_window(workload, params, halo, fill, rows, cols, iters, 0, rows, broken)
         assert not bad["ok"] and bad["rel_max_norm"] > 1e-5
+    if oracle.cpu_has_fma():
+        monkeypatch.setenv("STST_STRICT", "0")
+        record = bench.check_parity_window(workload, params, halo, fill, rows, cols, iters, 0, rows, whole)
+        assert "contracting" in record["oracle_arithmetic"]
+        assert record["rel_max_norm_vs_uncontracted_oracle"] == 0.0
+        assert record["rel_max_norm"] <= 1e-5       # FMA vs two roundings after 12 iterations
 
 
 NCU_CSV = '''==PROF== Connected to process 4242 (/usr/bin/python3.12)
