@@ -11,6 +11,9 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#if defined(__linux__)
+    #include <sys/mman.h>
+#endif
 
 #include <algorithm>
 #include <atomic>
@@ -239,6 +242,7 @@ namespace {
 std::mutex g_pinned_mutex;
 std::multimap<size_t, void *> g_pinned_free;
 std::unordered_map<void *, size_t> g_pinned_size;
+std::unordered_map<void *, size_t> g_pinned_registered; ///< blocks pinned piecewise: rounded size
 size_t g_pinned_cached_bytes = 0;
 
 size_t pinned_cache_limit() {
@@ -277,12 +281,70 @@ int stst_malloc_host(size_t bytes, void **ptr) {
         // Out of pinnable memory: drop the cache and retry once.
         (void)cudaGetLastError();
         (void)stst_host_cache_trim();
-        STST_CUDA(cudaHostAlloc(ptr, bytes, cudaHostAllocPortable));
+        err = cudaHostAlloc(ptr, bytes, cudaHostAllocPortable);
+    }
+    if (err != cudaSuccess) {
+        // Some hosts refuse one large cudaHostAlloc but accept the same pages registered piecewise:
+        // ordinary memory (2 MiB aligned, transparent huge pages requested), first touched by THIS
+        // thread — so that it lands on the NUMA node the caller is bound to — and page-locked in
+        // chunks of at most 1 GiB. All or nothing: a refused chunk undoes the others.
+        (void)cudaGetLastError();
+        constexpr size_t huge = size_t(2) << 20, chunk = size_t(1) << 30;
+        const size_t rounded = (bytes + huge - 1) / huge * huge;
+        void *block = std::aligned_alloc(huge, rounded);
+        if (!block)
+            return fail(-1, "stst_malloc_host", "out of host memory");
+#if defined(__linux__) && defined(MADV_HUGEPAGE)
+        (void)madvise(block, rounded, MADV_HUGEPAGE);
+#endif
+        std::memset(block, 0, rounded);
+        size_t done = 0;
+        for (; done < rounded; done += chunk) {
+            const size_t n = std::min(chunk, rounded - done);
+            if (cudaHostRegister(static_cast<char *>(block) + done, n, cudaHostRegisterPortable) !=
+                cudaSuccess)
+                break;
+        }
+        if (done < rounded) {
+            const cudaError_t why = cudaGetLastError();
+            for (size_t off = 0; off < done; off += chunk)
+                (void)cudaHostUnregister(static_cast<char *>(block) + off);
+            std::free(block);
+            return fail(int(why ? why : cudaErrorMemoryAllocation), "stst_malloc_host",
+                        "cudaHostAlloc and piecewise cudaHostRegister both refused the request");
+        }
+        *ptr = block;
+        std::lock_guard<std::mutex> lock(g_pinned_mutex);
+        g_pinned_size[*ptr] = bytes;
+        g_pinned_registered[*ptr] = rounded;
+        return 0;
     }
     std::lock_guard<std::mutex> lock(g_pinned_mutex);
     g_pinned_size[*ptr] = bytes;
     return 0;
 }
+
+namespace {
+/// Give a block back to the system: cudaFreeHost, or unregister + free for piecewise-registered ones.
+cudaError_t release_pinned_block(void *ptr) {
+    size_t registered = 0;
+    {
+        std::lock_guard<std::mutex> lock(g_pinned_mutex);
+        auto it = g_pinned_registered.find(ptr);
+        if (it != g_pinned_registered.end()) {
+            registered = it->second;
+            g_pinned_registered.erase(it);
+        }
+    }
+    if (registered == 0)
+        return cudaFreeHost(ptr);
+    constexpr size_t chunk = size_t(1) << 30;
+    for (size_t off = 0; off < registered; off += chunk)
+        (void)cudaHostUnregister(static_cast<char *>(ptr) + off);
+    std::free(ptr);
+    return cudaSuccess;
+}
+} // namespace
 
 int stst_free_host(void *ptr) {
     if (!ptr)
@@ -298,7 +360,7 @@ int stst_free_host(void *ptr) {
         if (it != g_pinned_size.end())
             g_pinned_size.erase(it);
     }
-    STST_CUDA(cudaFreeHost(ptr));
+    STST_CUDA(release_pinned_block(ptr));
     return 0;
 }
 
@@ -312,7 +374,7 @@ int stst_host_cache_trim(void) {
             g_pinned_size.erase(b.second);
     }
     for (auto const &b : blocks)
-        (void)cudaFreeHost(b.second);
+        (void)release_pinned_block(b.second);
     return 0;
 }
 

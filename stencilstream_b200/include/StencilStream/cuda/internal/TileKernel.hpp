@@ -69,8 +69,35 @@ template <typename Cell, int CW> constexpr bool lane_major_tiles() {
     return false;
 #else
     using L = CellLayout<Cell>;
-    return (CW == 4 || CW == 8) && L::n_planes == 1 && L::plane_bytes(0) == 4;
+    if (!(CW == 4 || CW == 8))
+        return false;
+    // ONE evolving 4-byte plane (Jacobi's float; HotSpot's `temp`), plus any number of 4-byte planes
+    // the cell type declares constant (`Cell::constant_fields`: HotSpot's `power`). Declared planes
+    // pass through the sweeps untouched, i.e. they are never rewritten and so can never be
+    // converted: they stay in the natural layout TMA delivers and are read with one 128-bit load per
+    // row (plus, if a functor does read a neighbour's constant, the natural layout's edge loads),
+    // while the evolving plane gets the conflict-free lane-major rows — for HotSpot 6 + 4 instead of
+    // 12 + 4 shared-memory wavefronts per row and warp.
+    const unsigned constant = constant_fields_mask<Cell>();
+    unsigned evolving = 0;
+    for (std::size_t i = 0; i < L::n_planes; i++) {
+        if (L::plane_bytes(i) != 4)
+            return false;
+        if (!((constant >> i) & 1u))
+            evolving++;
+    }
+  #if defined(STST_NO_MIXED_LANE_MAJOR)
+    return L::n_planes == 1;
+  #else
+    return evolving == 1;
+  #endif
 #endif
+}
+
+/// Whether plane I of a lane-major kernel is stored lane-major (the evolving plane) or natural (the
+/// declared-constant ones).
+template <typename Cell, std::size_t I> constexpr bool plane_is_lane_major() {
+    return ((constant_fields_mask<Cell>() >> I) & 1u) == 0;
 }
 
 /// Neighbourhood acquisition strategies of sweep_rows.
@@ -524,7 +551,7 @@ sweep_rows(F const &tf, typename F::Cell const &halo_value,
         for_each_plane<Cell>([&](auto I) {
             using T = typename L::template plane_t<I>;
             const T *rp = in.template plane<I>() + row * cols;
-            if constexpr (kInLaneMajor) {
+            if constexpr (kInLaneMajor && plane_is_lane_major<Cell, I>()) {
                 // see lane_major_tiles(): all conflict-free scalar loads
                 const T *q = rp + tx;
 #pragma unroll
@@ -641,7 +668,7 @@ sweep_rows(F const &tf, typename F::Cell const &halo_value,
                     if ((spec.keep >> I) & 1u)
                         return; // passes through: `out` aliases `in` for this plane
                 }
-                if constexpr (kOutLaneMajor) {
+                if constexpr (kOutLaneMajor && plane_is_lane_major<Cell, I>()) {
                     T *o = out.template plane<I>() + y * cols + tx;
 #pragma unroll
                     for (int i = 0; i < CW; i++)
