@@ -96,11 +96,29 @@ template <typename Cell> constexpr int max_threads_per_cta() {
     if (sizeof(Cell) <= 8)
         return STST_LIGHT_MAX_THREADS;
 #endif
+    // Cells of tens of bytes (FDTD: 32) re-read their neighbourhood from shared memory and are
+    // latency-bound at 8 warps per SM; their kernels need ~150 registers, which still allows 12
+    // warps: 384 threads measured +3.5 % over 256 (FDTD max_grid 99.7 -> 103.3 GCell-updates/s;
+    // 320: 102.8; 512 forces spills: +1 %; profiles/r02_variants_fdtd_threads.txt).
+    if (sizeof(Cell) > 16 && sizeof(Cell) <= 64) {
 #if defined(STST_MID_MAX_THREADS)
-    if (sizeof(Cell) > 16 && sizeof(Cell) <= 64)
         return STST_MID_MAX_THREADS;
+#else
+        return 384;
 #endif
-    return (sizeof(Cell) > 64 && column_group_width<Cell>() == 1) ? 512 : 256;
+    }
+    // Very fat cells (mantle convection, 88 bytes of doubles), one column per thread: the kernel is
+    // bound by the latency of dependent fp64 chains (15 divisions per cell-iteration), so warps count.
+    // 640 threads (20 warps, 92 registers, no spills) measured 9.69 against 9.17 GCell-updates/s with
+    // 512 (98 registers); 768 (80 registers) 8.95 (profiles/r02_variants_convection_threads.txt).
+    if (sizeof(Cell) > 64 && column_group_width<Cell>() == 1) {
+#if defined(STST_FAT_MAX_THREADS)
+        return STST_FAT_MAX_THREADS;
+#else
+        return 640;
+#endif
+    }
+    return 256;
 }
 
 /// blockDim.x the sweep kernel is compiled for, or 0 if it is a run-time choice. Cells that use
@@ -254,7 +272,11 @@ LaunchPlan make_plan(int device, unsigned grid_h, unsigned grid_w, std::size_t n
     // Cost model in "HBM-byte equivalents" per cell-iteration.
     const double hbm_bytes = 2.0 * double(sizeof(Cell)) * n_sub; // one read + one write / sweep
     // on-chip work per cell-iteration, fitted to measured sweeps (profiles/r01_sweep_*.log)
-    const double onchip = 0.475 * double(sizeof(Cell)) * n_sub + 0.4 * n_sub;
+    // ... and with the stencil radius (window loads and functor work per cell): without this factor
+    // the radius-3 star was planned at k = 3 (793 GCell-updates/s) where k = 2 runs at 839, and the
+    // radius-2 star at k = 3 instead of 4 (profiles/r02_sweep_jacobi_r{2,3}.log)
+    const double onchip = (0.475 * double(sizeof(Cell)) * n_sub + 0.4 * n_sub) *
+                          (1.0 + 0.4 * double(radius - 1));
     if (fused_override > 0) {
         // `fused_iterations` is an upper bound: take the deepest fusion not exceeding it whose tile
         // still fits into shared memory — split between `ctas_per_sm` CTAs or given to one,
