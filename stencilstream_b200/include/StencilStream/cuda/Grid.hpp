@@ -263,6 +263,9 @@ template <typename Cell> class GridStorage {
     template <bool scatter>
     void launch_layout_kernel(Cell *staging, std::size_t plane_row0, std::size_t cells) {
 #if defined(__CUDACC__)
+        int current_device = -1;
+        if (cudaGetDevice(&current_device) != cudaSuccess || current_device != device)
+            cudaSetDevice(device); // the stream belongs to this grid's device
         const unsigned block = 256;
         const unsigned grid =
             unsigned(std::min<std::size_t>((cells + block - 1) / block, std::size_t(148) * 16));

@@ -682,6 +682,9 @@ template <concepts::TransitionFunction F, bool split_cell_structure = false> cla
                 }
                 allow(me, source.device);
                 allow(source.device, me);
+                // (a CUDA event belongs to the device that is current when it is created, and can
+                // only be recorded on that device's streams)
+                STST_RT_CHECK(stst_set_device(me));
                 set->done.push_back(std::make_unique<Event>());
             }
             set->speculating = speculation_enabled();
@@ -713,6 +716,7 @@ template <concepts::TransitionFunction F, bool split_cell_structure = false> cla
         GridImpl result = source_grid.make_similar();
         auto &target = result.get_storage();
         target.allocate_device();
+        STST_RT_CHECK(stst_set_device(source.device)); // `ready` and the profiling events live there
         Event ready;
         const std::size_t k = shards->slabs.front()->get_plan().fused_iterations;
         std::size_t launches_before = 0;
@@ -770,6 +774,8 @@ template <concepts::TransitionFunction F, bool split_cell_structure = false> cla
         for (auto &slab : shards->slabs)
             launches_after += slab->get_n_launches();
         n_launches += launches_after - launches_before;
+        // leave the thread on the grid's device, as a single-device update does
+        STST_RT_CHECK(stst_set_device(source.device));
         return result;
     }
 
@@ -789,6 +795,7 @@ template <concepts::TransitionFunction F, bool split_cell_structure = false> cla
 
         std::shared_ptr<Event> start, stop;
         if (params.profiling) {
+            STST_RT_CHECK(stst_set_device(src.device)); // events belong to the current device
             start = std::make_shared<Event>(true);
             stop = std::make_shared<Event>(true);
             start->record(src.stream);

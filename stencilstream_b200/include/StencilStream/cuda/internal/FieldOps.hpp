@@ -191,6 +191,9 @@ inline void reduce_max_abs(int device, stst_stream_t stream, PlaneSet const &pla
         dev_keys = device_alloc(device, bytes, stream);
         STST_RT_CHECK(stst_memset_async(dev_keys, 0, bytes, stream));
         if (max_rows > 0) {
+            int current_device = -1;
+            if (cudaGetDevice(&current_device) != cudaSuccess || current_device != device)
+                cudaSetDevice(device); // the stream belongs to `device`
             const unsigned ctas = std::min<unsigned>(max_rows, 148u * 8u);
             reduce_max_abs_kernel<Cell>
                 <<<ctas, reduce_block_threads, 0, static_cast<cudaStream_t>(stream)>>>(

@@ -234,8 +234,9 @@ template <typename F> class SlabUpdate {
     void backup() {
         join_streams();
         // the ghost rows of the current generation are complete once the neighbours have raised
-        // this epoch's flags — the same condition a pass waits for
-        for (int s = 0; s < 2; s++) {
+        // this epoch's flags — the same condition a pass waits for (with the NCCL transport the
+        // receive that filled them is already ordered before this point by join_streams())
+        for (int s = 0; s < 2 && !nccl_comm; s++) {
             if (has_side(s))
                 STST_RT_CHECK(stst_stream_wait_value32_geq(interior_stream, my_flag(s),
                                                            unsigned(epoch + 1)));
@@ -450,7 +451,7 @@ template <typename F> class SlabUpdate {
         // overwritten: wait until those pushes have landed (the condition a pass waits for).
         // (A slab that has never run a pass or an exchange has no such pushes pending — and flags
         // that still read zero.)
-        for (int s = 0; s < 2 && epoch > 0; s++) {
+        for (int s = 0; s < 2 && epoch > 0 && !nccl_comm; s++) {
             if (has_side(s))
                 STST_RT_CHECK(stst_stream_wait_value32_geq(interior_stream, my_flag(s),
                                                            unsigned(epoch + 1)));
