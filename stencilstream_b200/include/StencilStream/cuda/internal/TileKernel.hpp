@@ -623,8 +623,26 @@ sweep_rows(F const &tf, typename F::Cell const &halo_value,
                 in_grid = gy >= 0 && gy < int(geo.grid_h) && gx >= 0 && gx < int(geo.grid_w);
             }
             if (in_grid) {
-                StencilImpl st(sycl::id<2>(std::size_t(unsigned(gy)), std::size_t(unsigned(gx))),
-                               sycl::range<2>(geo.grid_h, geo.grid_w), iteration, SUB, tdv);
+                const std::size_t id_r = std::size_t(unsigned(gy)), id_c = std::size_t(unsigned(gx));
+                const std::size_t range_r = geo.grid_h, range_c = geo.grid_w;
+                if constexpr (kInterior) {
+                    // Every cell an interior tile computes — exact or not — lies at least one cell
+                    // inside the grid (fused_sweep_kernel admits a tile to this path only if its
+                    // staged footprint does). Telling the compiler lets it fold the border tests
+                    // functors make on `stencil.id` / `stencil.grid_range` (HotSpot's adiabatic
+                    // borders, reference examples/hotspot/hotspot.cpp:77-87: four compares and four
+                    // selects per cell) out of the interior path; border tiles keep them.
+                    __builtin_assume(id_r != 0);
+                    __builtin_assume(id_r != range_r - 1);
+                    __builtin_assume(id_r < range_r - 1);
+                    __builtin_assume(id_r + 1 < range_r);
+                    __builtin_assume(id_c != 0);
+                    __builtin_assume(id_c != range_c - 1);
+                    __builtin_assume(id_c < range_c - 1);
+                    __builtin_assume(id_c + 1 < range_c);
+                }
+                StencilImpl st(sycl::id<2>(id_r, id_c), sycl::range<2>(range_r, range_c), iteration,
+                               SUB, tdv);
 #pragma unroll
                 for (int sr = 0; sr < D; sr++) {
 #pragma unroll
@@ -975,9 +993,13 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
     const int gy0 = tile_gy - int(geo.halo);
     const int gx0 = tile_gx - int(geo.hpad);
 
+    // Interior: the staged footprint lies inside the grid, with at least one column to spare on
+    // either side (rows: every computed row is >= radius rows away from the footprint's edge
+    // anyway) — so that ALL cells the tile computes, including the never-exact outermost columns,
+    // are at least one cell inside the grid (see the __builtin_assume in sweep_rows).
     const bool interior = gy0 >= 0 && tile_gy + int(geo.tile_h + geo.halo) <= int(geo.grid_h) &&
-                          tile_gy + int(geo.tile_h) <= out_hi && gx0 >= 0 &&
-                          tile_gx + int(geo.tile_w + geo.hpad) <= int(geo.grid_w);
+                          tile_gy + int(geo.tile_h) <= out_hi && gx0 >= 1 &&
+                          tile_gx + int(geo.tile_w + geo.hpad) + 1 <= int(geo.grid_w);
 
     if (interior) {
         run_tile<F, CW, true, kMode, kTX, kSpec>(tf, halo_value, tdvs, src, dst, push, maps, geo, smem,
