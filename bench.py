@@ -281,7 +281,7 @@ def time_cpu_oracle(workload: str, rows: int, cols: int, total_rows: int | None 
     }, elapsed
 
 
-def time_rodinia_hotspot(size: int = 1024, iterations: int = 200):
+def time_rodinia_hotspot(size: int = 2048, iterations: int = 400):
     """Second, independent CPU baseline for HotSpot: the reference's Rodinia OpenMP program
     (examples/hotspot/hotspot_openmp.cpp, compiled in place into oracle/_ref/hotspot_openmp by
     oracle/recipes.py) on a size x size grid. Returns None where the binary does not exist."""
@@ -358,9 +358,11 @@ def check_parity_window(workload, params, halo, fill, total_rows, cols, iters, r
     checker = contracted or oracle.best()
     other = oracle.best() if contracted is not None else None
     cores = oracle.set_threads()
-    band = np.empty((r1 - r0, cols), dtype=cells.dtype)
-    fill(band, r0, r1, total_rows)
-    crop = np.ascontiguousarray(band[:, k0:k1])
+    # (generated from a multiple of 1024 rows on: the Conway soup is seeded per 1024-row band)
+    g0 = r0 - r0 % 1024
+    band = np.empty((r1 - g0, cols), dtype=cells.dtype)
+    fill(band, g0, r1, total_rows)
+    crop = np.ascontiguousarray(band[r0 - g0:, k0:k1])
     del band
     t0 = time.perf_counter()
     want = checker.run_window2d(workload, params, halo, crop, r0, k0, total_rows, cols, 0, iters)

@@ -12,10 +12,12 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
 # (workload, rows, cols, fused iterations, summary file under profiles/)
 CAPTURES = [
-    ("jacobi5", 16384, 16384, 6, "r01_s3_ncu_jacobi5_k6_summary.txt"),
-    ("hotspot", 16384, 16384, 4, "r01_s3_ncu_hotspot_passthrough_summary.txt"),
-    ("fdtd", 4608, 4608, 3, "r01_s3_ncu_fdtd_passthrough_summary.txt"),
-    ("convection_pt", 4096, 8192, 1, "r01_s3_ncu_convection_pt_summary.txt"),
+    # round 2, final kernels (scripts/gpu_job_ncu.sh)
+    ("jacobi5", 16384, 16384, 6, "r02_final_ncu_jacobi5_summary.txt"),
+    ("hotspot", 16384, 16384, 4, "r02_final_ncu_hotspot_summary.txt"),
+    ("fdtd", 4608, 4608, 4, "r02_final_ncu_fdtd_summary.txt"),
+    ("convection_pt", 4096, 8192, 1, "r02_final_ncu_convection_pt_summary.txt"),
+    ("jacobi_r3", 16384, 16384, 2, "r02_final_ncu_jacobi_r3_summary.txt"),
 ]
 SCALE = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 

@@ -273,10 +273,10 @@ LaunchPlan make_plan(int device, unsigned grid_h, unsigned grid_w, std::size_t n
     const double hbm_bytes = 2.0 * double(sizeof(Cell)) * n_sub; // one read + one write / sweep
     // on-chip work per cell-iteration, fitted to measured sweeps (profiles/r01_sweep_*.log)
     // ... and with the stencil radius (window loads and functor work per cell): without this factor
-    // the radius-3 star was planned at k = 3 (793 GCell-updates/s) where k = 2 runs at 839, and the
-    // radius-2 star at k = 3 instead of 4 (profiles/r02_sweep_jacobi_r{2,3}.log)
+    // the radius-3 star was planned at k = 3 (793 GCell-updates/s) where k = 2 runs at 839; the
+    // radius-2 star must stay at k = 4 (1174; k = 3: 1142) — profiles/r02_sweep_jacobi_r{2,3}.log
     const double onchip = (0.475 * double(sizeof(Cell)) * n_sub + 0.4 * n_sub) *
-                          (1.0 + 0.4 * double(radius - 1));
+                          (1.0 + 0.28 * double(radius - 1));
     if (fused_override > 0) {
         // `fused_iterations` is an upper bound: take the deepest fusion not exceeding it whose tile
         // still fits into shared memory — split between `ctas_per_sm` CTAs or given to one,

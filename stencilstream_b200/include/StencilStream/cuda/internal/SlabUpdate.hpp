@@ -53,6 +53,7 @@
 #include <cstdlib>
 #include <memory>
 #include <stdexcept>
+#include <string>
 #include <vector>
 
 namespace stencil {
@@ -778,12 +779,24 @@ template <typename F> class SlabUpdate {
             n_launches++;
         };
 
-        const bool split = cfg.overlap && neighbours && owned_rows() > 2 * ghost;
-        if (split) {
+        // How a pass is launched (cfg.overlap; STST_SLAB_PASS=split|single overrides):
+        //   single (default) — ONE launch over the whole slab whose tile rows are ordered boundary
+        //     first: the rows the neighbours wait for are computed, pushed and signalled by the first
+        //     wave of CTAs while the rest of the launch is still running, so the exchange overlaps the
+        //     interior exactly as with separate launches, but without strip tiles that stage
+        //     `strip + 2 halo` rows for `strip` rows of output, without a second launch competing for
+        //     SMs, and with one launch per pass (measured: FDTD 4608^2 on 8 GPUs 594 -> see DESIGN.md);
+        //   split — boundary strips in one launch on the high-priority stream, interior in another
+        //     (round 1 and first half of round 2);
+        //   no overlap (cfg.overlap false) — one launch in natural order, flags at its very end.
+        static const int pass_mode = [] {
+            const char *env = std::getenv("STST_SLAB_PASS");
+            return (env && std::string(env) == "split") ? 1 : 0;
+        }();
+        const bool can_split = cfg.overlap && neighbours && owned_rows() > 2 * ghost;
+        if (can_split && (pass_mode == 1 || nccl_comm)) {
             // Two launches per pass: both boundary strips (with the halo push and the flags), then
-            // the interior. (Until round 2 this was five: a launch per strip and a one-thread kernel
-            // per flag, each ~7 us of host time and, worse, four dependent launches on the path
-            // between neighbouring slabs — what limited strong scaling to small slabs.)
+            // the interior. (The NCCL transport needs the strips finished before it can send them.)
             const std::size_t top_hi = has_up() ? cfg.row_lo + ghost : cfg.row_lo;
             const std::size_t bottom_lo = has_down() ? cfg.row_hi - ghost : cfg.row_hi;
             sweep(cfg.row_lo, top_hi, bottom_lo, cfg.row_hi, true, true, boundary_stream);
@@ -791,7 +804,13 @@ template <typename F> class SlabUpdate {
                 nccl_exchange(cur ^ 1); // strips out, ghost rows of the next generation in
             sweep(top_hi, bottom_lo, 0, 0, false, false, interior_stream);
         } else {
+            if (cfg.overlap && pushes) {
+                region.boundary_first = true;
+                region.push_rows_top = has_up() ? unsigned(ghost) : 0u;
+                region.push_rows_bottom = has_down() ? unsigned(ghost) : 0u;
+            }
             sweep(cfg.row_lo, cfg.row_hi, 0, 0, true, false, boundary_stream);
+            region.boundary_first = false;
             if (nccl_comm)
                 nccl_exchange(cur ^ 1);
         }
