@@ -780,18 +780,19 @@ template <typename F> class SlabUpdate {
         };
 
         // How a pass is launched (cfg.overlap; STST_SLAB_PASS=split|single overrides):
-        //   single (default) — ONE launch over the whole slab whose tile rows are ordered boundary
-        //     first: the rows the neighbours wait for are computed, pushed and signalled by the first
-        //     wave of CTAs while the rest of the launch is still running, so the exchange overlaps the
-        //     interior exactly as with separate launches, but without strip tiles that stage
-        //     `strip + 2 halo` rows for `strip` rows of output, without a second launch competing for
-        //     SMs, and with one launch per pass (measured: FDTD 4608^2 on 8 GPUs 594 -> see DESIGN.md);
-        //   split — boundary strips in one launch on the high-priority stream, interior in another
-        //     (round 1 and first half of round 2);
+        //   split (default) — both boundary strips in ONE launch on the high-priority stream (it waits
+        //     for the neighbours' flags, pushes, and its last CTA raises their flags), the interior in
+        //     another launch that needs no flag at all: two launches per pass;
+        //   single — ONE launch over the whole slab whose tile rows are ordered boundary first, the
+        //     flags raised by the last boundary CTA. No strip tiles (which stage `strip + 2 halo` rows
+        //     for `strip` rows of output) and one launch fewer — but the WHOLE pass then waits for the
+        //     neighbours' flags, so any skew between the slabs stalls interior work that the split
+        //     form lets run: measured slower on 8 GPUs (FDTD 4608^2 565 vs 596, HotSpot 16384^2 5618
+        //     vs 5766 GCell-updates/s, profiles/r02_pass_ab_8gpu_*.json). Kept selectable;
         //   no overlap (cfg.overlap false) — one launch in natural order, flags at its very end.
         static const int pass_mode = [] {
             const char *env = std::getenv("STST_SLAB_PASS");
-            return (env && std::string(env) == "split") ? 1 : 0;
+            return (env && std::string(env) == "single") ? 0 : 1;
         }();
         const bool can_split = cfg.overlap && neighbours && owned_rows() > 2 * ghost;
         if (can_split && (pass_mode == 1 || nccl_comm)) {
