@@ -10,5 +10,5 @@ for w in jacobi_r2 jacobi_r3 conway hotspot fdtd convection_pt; do
 done
 kill $SMI
 (time timeout 400 python bench.py --impl reference --steps 3 --warmup 1) > $out/bench_reference_arm.json 2> $out/bench_reference_arm.err
-bash scripts/gpu_job_ncu.sh > $out/ncu_job.log 2>&1
+bash scripts/gpu/ncu_captures.sh > $out/ncu_job.log 2>&1
 grep -E "passed|failed|FAILED|rc=" $out/pytest_gpu.log | tail -5; tail -c 400 $out/bench_default.err; tail -5 $out/ncu_job.log

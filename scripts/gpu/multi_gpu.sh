@@ -1,5 +1,5 @@
 #!/bin/bash
-# usage: bash scripts/gpu_job_multi.sh N   (run under `gpurun --gpus N`)
+# usage: bash scripts/gpu/multi_gpu.sh N   (run under `gpurun --gpus N`)
 N=${1:-2}
 out=gpurun_out/r02_n$N; mkdir -p $out
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517"

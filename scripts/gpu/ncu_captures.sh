@@ -20,6 +20,10 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
     python bench.py --workload jacobi5 --iterations 300 --steps 1 --warmup 1 --no-cpu-baseline > $out/launches_bench_jacobi5.log 2>&1
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/launches_bench_hotspot.csv \
     python bench.py --workload hotspot --iterations 200 --steps 1 --warmup 1 --no-cpu-baseline > $out/launches_bench_hotspot.log 2>&1
+# one pass over the eight 576-row slabs of the FDTD max_grid grid, all on this GPU (what a slab pass consists of
+# and what its launches cost: profiles/r02_launches_fdtd_8_slabs_one_gpu.csv)
+timeout 150 ncu --metrics gpu__time_duration.sum --clock-control none -s 64 -c 160 --csv --log-file $out/launches_fdtd_8_slabs_one_gpu.csv \
+    python scripts/run_one.py --workload fdtd --rows 4608 --cols 4608 --iters 45 --calls 1 --devices 0,0,0,0,0,0,0,0 > $out/launches_fdtd_8_slabs_one_gpu.log 2>&1
 # the reference drivers' figures through the scraper
 for w in jacobi5 hotspot fdtd convection_pt; do
   mkdir -p $out/driver_$w

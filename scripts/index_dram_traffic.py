@@ -12,7 +12,7 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
 # (workload, rows, cols, fused iterations, summary file under profiles/)
 CAPTURES = [
-    # round 2, final kernels (scripts/gpu_job_ncu.sh)
+    # round 2, final kernels (scripts/gpu/ncu_captures.sh)
     ("jacobi5", 16384, 16384, 6, "r02_final_ncu_jacobi5_summary.txt"),
     ("hotspot", 16384, 16384, 4, "r02_final_ncu_hotspot_summary.txt"),
     ("fdtd", 4608, 4608, 4, "r02_final_ncu_fdtd_summary.txt"),
