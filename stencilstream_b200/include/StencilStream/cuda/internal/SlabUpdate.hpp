@@ -13,7 +13,7 @@
  * two complete plane sets (ping/pong) and two 32-bit flags in ONE cudaMalloc block, so that a single
  * IPC handle (or, within a process, a peer mapping) makes all of it addressable by the neighbours.
  *
- * One pass (= one fused launch over the slab, advancing it by n_gens <= k iterations), epoch e:
+ * One pass (two launches that together advance the slab by n_gens <= k iterations), epoch e:
  *
  *   boundary stream:  wait  flag_from_up >= e+1, flag_from_down >= e+1      (ghosts of epoch e in place)
  *                     wait  interior launch of epoch e-1
@@ -25,14 +25,15 @@
  *                     sweep the remaining rows (they depend on no ghost row)
  *
  * so the exchange for the next pass overlaps the interior sweep of this one, and nothing but the
- * two small boundary launches ever waits for a neighbour. Flags are waited for with
+ * small boundary launch ever waits for a neighbour (STST_SLAB_PASS=single selects a one-launch form,
+ * see pass()). Flags are waited for with
  * cuStreamWaitValue32 (stream-ordered, no host involvement, works across processes) and raised by the
  * boundary launch itself: every CTA fences its stores system-wide and takes an atomic ticket, the
  * holder of the last ticket stores the flags (exchange_halos(), which copies with cudaMemcpy, still
  * uses a one-thread kernel behind the copies). The flag protocol also
  * covers the write-after-read hazards of the ping/pong buffers: a neighbour can only write ghost rows
  * of buffer B in its epoch e+1 after it saw flag e+2, which is raised after this slab's epoch-e
- * boundary launches — the last readers of those ghost rows — have finished.
+ * boundary CTAs — the last readers of those ghost rows — have finished.
  *
  * Who provides the neighbours' addresses is not decided here: `attach()` takes raw pointers. Within a
  * process they come from another SlabUpdate (peer access enabled), across processes from

@@ -187,3 +187,71 @@ def run_group(world, workload, shape, offset, n, depth, mode):
         elif p.exitcode != 0:
             messages.append(f"worker exit code {p.exitcode}")
     assert not messages, "\n".join(messages)
+
+
+def _sequence_worker(rank, world, port, failures):
+    """Two sharded updates one after the other in the same process group (what bench.py's default
+    invocation does for its `workloads`): close() is collective and leaves the group usable."""
+    try:
+        sys.path.insert(0, str(ROOT))
+        sys.path.insert(0, str(ROOT / "tests"))
+        import torch.distributed as dist
+        import cases as cases_mod
+        import oracle
+        from fake_slab import HostSlab
+        from stencilstream_b200 import Params
+        from stencilstream_b200.sharding import ShardedStencilUpdate
+
+        os.environ["OMP_NUM_THREADS"] = "1"
+        dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank,
+                                world_size=world)
+        checker = oracle.port()
+        for workload, shape, n, depth in (("hotspot", (40, 30), 5, 2), ("jacobi5", (36, 28), 4, 3)):
+            params, halo, cells = cases_mod.make_case(workload, *shape, seed=5)
+            update = ShardedStencilUpdate(
+                workload, Params(transition_function=params, halo_value=halo, n_iterations=n,
+                                 blocking=True, fused_iterations=depth),
+                shape[0], shape[1], rank=rank, world=world, comm=dist,
+                slab_factory=lambda **kw: HostSlab(checker, depth, **kw))
+            update.load(cells[update.row_lo:update.row_hi])
+            update()
+            mine = update.to_numpy()
+            want = checker.run(workload, params, halo, cells, 0, n)
+            if mine.tobytes() != np.ascontiguousarray(want[update.row_lo:update.row_hi]).tobytes():
+                failures.put(f"rank {rank}: {workload} differs")
+            update.close()
+            update.close()          # idempotent
+            if update.slab is not None:
+                failures.put(f"rank {rank}: slab still there after close()")
+        try:
+            ShardedStencilUpdate("jacobi5", Params(n_iterations=1), 8, 8, rank=rank, world=world, comm=dist,
+                                 slab_factory=lambda **kw: HostSlab(checker, 1, **kw), transport="carrier-pigeon")
+            failures.put("an unknown transport was accepted")
+        except ValueError:
+            pass
+        dist.barrier()
+        dist.destroy_process_group()
+    except Exception:
+        failures.put(f"rank {rank}: {traceback.format_exc()}")
+
+
+def test_sharded_updates_can_follow_one_another(built):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    failures = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_sequence_worker, args=(r, 2, port, failures)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=180)
+    messages = []
+    while not failures.empty():
+        messages.append(failures.get())
+    for p in procs:
+        if p.is_alive():
+            p.kill()
+            messages.append("worker timed out")
+        elif p.exitcode != 0:
+            messages.append(f"worker exit code {p.exitcode}")
+    assert not messages, "\n".join(messages)
