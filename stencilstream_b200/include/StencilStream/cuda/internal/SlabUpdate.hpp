@@ -795,6 +795,12 @@ template <typename F> class SlabUpdate {
             const char *env = std::getenv("STST_SLAB_PASS");
             return (env && std::string(env) == "single") ? 0 : 1;
         }();
+        // Strips are `ghost` rows tall. Tile-high strips (no strip tile staging `ghost + 2 halo` rows
+        // for `ghost` rows of output) were measured too: a boundary CTA spends ~18 us in its
+        // system-scope fence and ticket whatever it computed (ncu, eight 576-row FDTD slabs: 84 strip
+        // CTAs 25 us, 84 full-tile CTAs 45 us, a wave of interior tiles 22-26 us), and 576 rows are
+        // 13.09 tile rows either way, so the taller strips only moved work into the launch that
+        // holds its SMs longest (N = 2: 197 vs 195 GCell-updates/s; not adopted).
         const bool can_split = cfg.overlap && neighbours && owned_rows() > 2 * ghost;
         if (can_split && (pass_mode == 1 || nccl_comm)) {
             // Two launches per pass: both boundary strips (with the halo push and the flags), then
